@@ -1,0 +1,124 @@
+"""ctypes binding of libo3dml_b200.so (the C ABI declared in include/o3dml_b200.h).
+
+There is NO CPU fallback: every entry point needs the CUDA library and a CUDA
+device, and fails loudly otherwise.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libo3dml_b200.so")
+_lib = None
+
+c_void_p, c_int, c_int64, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                               ctypes.c_float, ctypes.c_size_t)
+
+
+class Src(ctypes.Structure):
+    """o3dml_src_t"""
+    _fields_ = [("data", c_void_p), ("index", c_void_p), ("rows", c_int64),
+                ("out_rows_per_batch", c_int64), ("src_rows_per_batch", c_int64),
+                ("channels", ctypes.c_int32), ("ld", ctypes.c_int32),
+                ("index_is64", ctypes.c_int32), ("index_ld", ctypes.c_int32)]
+
+
+P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
+_SIGNATURES = {
+    "o3dml_abi_version": (c_int, []),
+    "o3dml_last_error": (ctypes.c_char_p, []),
+    "o3dml_voxelize_workspace_bytes": (Z, [L, L]),
+    "o3dml_voxelize": (I, [P, L, I, P, L, P, P, P, L, L, P, P, P, P, P, P, P, Z, P]),
+    "o3dml_ragged_to_dense": (I, [P, I, L, P, L, L, L, L, P, P]),
+    "o3dml_knn_workspace_bytes": (Z, [L, L, L]),
+    "o3dml_knn_search": (I, [P, L, P, P, L, P, L, I, P, I, P, P, Z, P]),
+    "o3dml_radius_workspace_bytes": (Z, [L, L, L]),
+    "o3dml_radius_count": (I, [P, L, P, P, L, P, L, F, P, P, P, Z, P]),
+    "o3dml_radius_fill": (I, [P, L, L, P, L, F, P, P, P, P, Z, P]),
+    "o3dml_pp_pfn_scatter": (I, [P, I, I, P, P, P, P, P, L, P, P, P, I, F, F, F, F, I, I, I, P, P,
+                                 I, P]),
+    "o3dml_linear": (I, [L, ctypes.POINTER(Src), I, P, P, P, P, I, I, F, P, I, I, I, P]),
+    "o3dml_conv3x3_nhwc": (I, [P, I, I, I, I, I, P, P, P, I, F, P, I, P]),
+    "o3dml_deconv_nhwc": (I, [P, I, I, I, I, I, P, P, P, I, F, P, I, I, P]),
+    "o3dml_randla_lfa_pool": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
+    "o3dml_gather_max": (I, [P, L, I, I, P, I, L, I, L, L, I, P, I, P]),
+    "o3dml_kpconv_gather": (I, [P, L, P, L, P, I, I, P, I, P, I, F, P, P]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+
+def lib():
+    """Loads (building first if the .so is absent and nvcc is available)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build
+            try:
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(
+                    "open3d_ml_b200: CUDA library %s is missing and could not be built (%s). "
+                    "There is no CPU fallback." % (LIB_PATH, e)) from e
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+        if h.o3dml_abi_version() != 1:
+            raise RuntimeError("open3d_ml_b200: ABI version mismatch")
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError("open3d_ml_b200: " + lib().o3dml_last_error().decode())
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("open3d_ml_b200: no CUDA device visible; this library has no CPU path")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def act_code(act):
+    return {None: 0, "none": 0, "relu": 1, "leaky": 2}[act]
+
+
+def make_src(data, index=None, index_ld=1, out_rows_per_batch=0, src_rows_per_batch=0,
+             channels=None, ld=None, rows=None):
+    """data: 2-D float32 CUDA tensor [rows, C] (row stride ld)."""
+    s = Src()
+    s.data = data.data_ptr()
+    s.rows = data.shape[0] if rows is None else rows
+    s.channels = data.shape[1] if channels is None else channels
+    s.ld = data.stride(0) if ld is None else ld
+    if index is not None:
+        assert index.dtype in (torch.int64, torch.int32) and index.is_cuda
+        s.index = index.data_ptr()
+        s.index_is64 = 1 if index.dtype == torch.int64 else 0
+        s.index_ld = index_ld
+    s.out_rows_per_batch = out_rows_per_batch
+    s.src_rows_per_batch = src_rows_per_batch
+    return s
+
+
+def linear(srcs, weight_t, out, scale=None, shift=None, residual=None, act=None, slope=0.0,
+           num_rows=None, out_channels=None, out_ld=None, out_nchw_plane=0):
+    """out[n,:] = act(scale * (concat(srcs)[n] @ weight_t) + shift + residual[n])."""
+    arr = (Src * len(srcs))(*srcs)
+    n = out.shape[0] if num_rows is None else num_rows
+    co = weight_t.shape[1] if out_channels is None else out_channels
+    ld = (out.stride(0) if out_nchw_plane == 0 else co) if out_ld is None else out_ld
+    check(lib().o3dml_linear(n, arr, len(srcs), ptr(weight_t), ptr(scale), ptr(shift),
+                             ptr(residual), residual.stride(0) if residual is not None else 0,
+                             act_code(act), float(slope), ptr(out), ld, co, out_nchw_plane,
+                             stream()))
+    return out

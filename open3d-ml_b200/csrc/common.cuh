@@ -1,0 +1,98 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libo3dml_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define O3DML_OK 0
+#define O3DML_ERR_INVALID 1
+#define O3DML_ERR_WORKSPACE 2
+#define O3DML_ERR_CUDA 3
+#define O3DML_ERR_UNSUPPORTED 4
+
+extern "C" void o3dml_set_error(const char* fmt, ...);
+
+#define O3DML_FAIL(code, ...)      \
+    do {                           \
+        o3dml_set_error(__VA_ARGS__); \
+        return (code);             \
+    } while (0)
+
+#define O3DML_CHECK(cond, ...)                               \
+    do {                                                     \
+        if (!(cond)) O3DML_FAIL(O3DML_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define O3DML_CUDA(expr)                                                              \
+    do {                                                                              \
+        cudaError_t e__ = (expr);                                                     \
+        if (e__ != cudaSuccess)                                                       \
+            O3DML_FAIL(O3DML_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+                       cudaGetErrorString(e__), __FILE__, __LINE__);                  \
+    } while (0)
+
+#define O3DML_LAUNCH_CHECK() O3DML_CUDA(cudaGetLastError())
+
+namespace o3dml {
+
+constexpr int kNumSMs = 148;  // B200
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) {
+    return (a + b - 1) / b;
+}
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace.
+struct Workspace {
+    char* base;
+    size_t size, off;
+    bool ok;
+    Workspace(void* p, size_t n) : base((char*)p), size(n), off(0), ok(true) {}
+    template <typename T>
+    T* take(size_t count) {
+        size_t bytes = align_up(count * sizeof(T));
+        if (!base || off + bytes > size) {
+            ok = false;
+            off += bytes;
+            return nullptr;
+        }
+        T* r = (T*)(base + off);
+        off += bytes;
+        return r;
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// float32 squared distance with the operation order of the op contract
+// (oracle/ops_ref.c sqdist3): ((dx*dx + dy*dy) + dz*dz), no FMA contraction.
+__device__ __forceinline__ float sqdist3(float qx, float qy, float qz, float px, float py,
+                                         float pz) {
+    float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ int64_t load_index(const void* p, int64_t i, int is64) {
+    return is64 ? ((const int64_t*)p)[i] : (int64_t)((const int32_t*)p)[i];
+}
+
+// activation codes shared with the C ABI
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_LEAKY) return v >= 0.f ? v : v * slope;
+    return v;
+}
+
+}  // namespace o3dml

@@ -1,0 +1,251 @@
+"""Host-side mirror of ``open3d.ml.torch.ops`` / ``open3d.ml.torch.layers`` /
+``open3d.core.nns`` for the operators on the hot path,
+backed by the sm_100a kernels of libo3dml_b200.so.
+
+Same names, argument meaning, result field names and error behaviour
+(RuntimeError) as the interface the reference's models call:
+
+    voxelize          ml3d/torch/models/point_pillars.py:354-357
+    ragged_to_dense   point_pillars.py:364-366, kpconv.py:2030-2032
+    knn_search        ml3d/torch/models/point_transformer.py:724-734
+    FixedRadiusSearch ml3d/torch/models/kpconv.py:2021-2026
+    NearestNeighborSearch  ml3d/datasets/utils/dataprocessing.py:99-103
+
+Inputs may live on the CPU (the reference's dataloaders call these ops with
+numpy-backed tensors): they are copied to the current CUDA device, the kernels
+run there, and the results come back on the input's device.  There is no CPU
+implementation.
+"""
+import collections
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+VoxelizeResult = collections.namedtuple(
+    "VoxelizeResult",
+    "voxel_coords voxel_point_indices voxel_point_row_splits voxel_batch_splits")
+KnnResult = collections.namedtuple("KnnSearchResult",
+                                   "neighbors_index neighbors_row_splits neighbors_distance")
+RadiusResult = collections.namedtuple("FixedRadiusSearchResult",
+                                      "neighbors_index neighbors_row_splits neighbors_distance")
+
+INT64_MAX = 2**63 - 1
+
+
+def _dev(t):
+    L.require_cuda()
+    return t if t.is_cuda else t.cuda(non_blocking=True)
+
+
+def _host3(x, what):
+    a = np.ascontiguousarray(torch.as_tensor(x).detach().cpu().numpy(), dtype=np.float32).reshape(-1)
+    if a.size != 3:
+        raise RuntimeError("%s must have 3 elements, got %d" % (what, a.size))
+    return a
+
+
+def _check_points(points, name="points"):
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise RuntimeError("%s must have shape [N,3], got %s" % (name, tuple(points.shape)))
+    if points.dtype != torch.float32:
+        raise RuntimeError("%s must be float32" % name)
+
+
+def _splits(row_splits, n, device):
+    if row_splits is None:
+        return torch.tensor([0, n], dtype=torch.int64, device=device)
+    if row_splits.dtype != torch.int64:
+        raise RuntimeError("row_splits must be int64")
+    return row_splits.to(device).contiguous()
+
+
+def voxelize_raw(points, row_splits, voxel_size, points_range_min, points_range_max,
+                 max_points_per_voxel, max_voxels, want_batch_id=False):
+    """Sync-free form: worst-case sized CUDA outputs + a device counter.
+    points may be a strided [N,3] view of an [N,C] tensor (last-dim stride 1)."""
+    _check_points(points)
+    points = _dev(points)
+    if points.stride(1) != 1:
+        points = points.contiguous()
+    n = points.shape[0]
+    dev = points.device
+    rs = _splits(row_splits, n, dev)
+    batch = rs.numel() - 1
+    vs, rmin, rmax = (_host3(voxel_size, "voxel_size"), _host3(points_range_min, "points_range_min"),
+                      _host3(points_range_max, "points_range_max"))
+    coords = torch.empty((n, 3), dtype=torch.int32, device=dev)
+    pidx = torch.empty((n,), dtype=torch.int64, device=dev)
+    vrs = torch.empty((n + 1,), dtype=torch.int64, device=dev)
+    bsp = torch.empty((batch + 1,), dtype=torch.int64, device=dev)
+    bid = torch.empty((n,), dtype=torch.int32, device=dev) if want_batch_id else None
+    counts = torch.empty((2,), dtype=torch.int64, device=dev)
+    wsb = L.lib().o3dml_voxelize_workspace_bytes(n, batch)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    L.check(L.lib().o3dml_voxelize(
+        L.ptr(points), n, points.stride(0), L.ptr(rs), batch, vs.ctypes.data, rmin.ctypes.data,
+        rmax.ctypes.data, int(min(max_points_per_voxel, INT64_MAX)), int(min(max_voxels, INT64_MAX)),
+        L.ptr(coords), L.ptr(pidx), L.ptr(vrs), L.ptr(bsp), L.ptr(bid), L.ptr(counts), L.ptr(ws),
+        wsb, L.stream()))
+    return coords, pidx, vrs, bsp, bid, counts
+
+
+def voxelize(points, row_splits, voxel_size, points_range_min, points_range_max,
+             max_points_per_voxel=INT64_MAX, max_voxels=INT64_MAX):
+    """open3d.ml.torch.ops.voxelize -- one device->host read (the voxel count)."""
+    was_cuda = points.is_cuda
+    coords, pidx, vrs, bsp, _, counts = voxelize_raw(points, row_splits, voxel_size,
+                                                     points_range_min, points_range_max,
+                                                     max_points_per_voxel, max_voxels)
+    m, kept = (int(v) for v in counts.tolist())
+    out = VoxelizeResult(coords[:m], pidx[:kept], vrs[:m + 1], bsp)
+    return out if was_cuda else VoxelizeResult(*(t.cpu() for t in out))
+
+
+def ragged_to_dense(values, row_splits, out_col_size, default_value, _add=0):
+    """open3d.ml.torch.ops.ragged_to_dense for integer / float32 values of shape [L] or [L, ...]."""
+    was_cuda = values.is_cuda
+    v = _dev(values).contiguous()
+    if v.element_size() not in (4, 8):
+        raise RuntimeError("ragged_to_dense: 4- or 8-byte element types only")
+    rs = _dev(row_splits)
+    if rs.dtype != torch.int64:
+        raise RuntimeError("row_splits must be int64")
+    rows = rs.numel() - 1
+    inner = 1
+    for s in v.shape[1:]:
+        inner *= s
+    out = torch.empty((rows, int(out_col_size)) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+    fill = torch.as_tensor(default_value).reshape(-1)[:1].to(v.dtype)
+    if v.dtype.is_floating_point:
+        if _add != 0:
+            raise RuntimeError("ragged_to_dense: add is for integer types")
+        bits = int(fill.view(torch.int32 if v.element_size() == 4 else torch.int64).item())
+    else:
+        bits = int(fill.item())
+    L.check(L.lib().o3dml_ragged_to_dense(L.ptr(v), v.element_size(), inner, L.ptr(rs), rows,
+                                          int(out_col_size), bits, int(_add), L.ptr(out), L.stream()))
+    return out if was_cuda else out.cpu()
+
+
+def knn_search(points, queries, k, points_row_splits=None, queries_row_splits=None,
+               index_dtype=torch.int32, metric="L2", ignore_query_point=False,
+               return_distances=False):
+    """open3d.ml.torch.ops.knn_search.  Rows ascend by (distance, index); distances are squared
+    L2 as upstream returns them for metric='L2'."""
+    if metric != "L2":
+        raise RuntimeError("knn_search: only metric='L2' is implemented")
+    if ignore_query_point:
+        raise RuntimeError("knn_search: ignore_query_point is not implemented")
+    _check_points(points), _check_points(queries, "queries")
+    was_cuda = points.is_cuda
+    p, q = _dev(points).contiguous(), _dev(queries).contiguous()
+    dev = p.device
+    ps, qs = _splits(points_row_splits, p.shape[0], dev), _splits(queries_row_splits, q.shape[0], dev)
+    batch = ps.numel() - 1
+    if qs.numel() - 1 != batch:
+        raise RuntimeError("knn_search: row splits disagree on the batch size")
+    k = int(k)
+    idx = torch.empty((q.shape[0], k), dtype=index_dtype, device=dev)
+    d2 = torch.empty((q.shape[0], k), dtype=torch.float32, device=dev) if return_distances else None
+    wsb = L.lib().o3dml_knn_workspace_bytes(p.shape[0], q.shape[0], batch)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    L.check(L.lib().o3dml_knn_search(L.ptr(p), p.shape[0], L.ptr(ps), L.ptr(q), q.shape[0],
+                                     L.ptr(qs), batch, k, L.ptr(idx),
+                                     1 if index_dtype == torch.int64 else 0, L.ptr(d2), L.ptr(ws),
+                                     wsb, L.stream()))
+    rs = torch.arange(0, (q.shape[0] + 1) * k, k, dtype=torch.int64, device=dev)
+    out = KnnResult(idx.reshape(-1), rs,
+                    d2.reshape(-1) if d2 is not None else torch.empty(0, device=dev))
+    return out if was_cuda else KnnResult(*(t.cpu() for t in out))
+
+
+def fixed_radius_search(points, queries, radius, points_row_splits=None, queries_row_splits=None,
+                        return_distances=True):
+    """Two-phase radius search (count, one device->host read of the total, fill)."""
+    _check_points(points), _check_points(queries, "queries")
+    was_cuda = points.is_cuda
+    p, q = _dev(points).contiguous(), _dev(queries).contiguous()
+    dev = p.device
+    ps, qs = _splits(points_row_splits, p.shape[0], dev), _splits(queries_row_splits, q.shape[0], dev)
+    batch = ps.numel() - 1
+    if qs.numel() - 1 != batch:
+        raise RuntimeError("fixed_radius_search: row splits disagree on the batch size")
+    nq = q.shape[0]
+    nrs = torch.empty((nq + 1,), dtype=torch.int64, device=dev)
+    total = torch.zeros((1,), dtype=torch.int64, device=dev)
+    wsb = L.lib().o3dml_radius_workspace_bytes(p.shape[0], nq, batch)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=dev)
+    L.check(L.lib().o3dml_radius_count(L.ptr(p), p.shape[0], L.ptr(ps), L.ptr(q), nq, L.ptr(qs),
+                                       batch, float(radius), L.ptr(nrs), L.ptr(total), L.ptr(ws),
+                                       wsb, L.stream()))
+    t = int(total.item())
+    idx = torch.empty((t,), dtype=torch.int32, device=dev)
+    d2 = torch.empty((t,), dtype=torch.float32, device=dev)
+    L.check(L.lib().o3dml_radius_fill(L.ptr(q), p.shape[0], nq, L.ptr(qs), batch, float(radius),
+                                      L.ptr(nrs), L.ptr(idx), L.ptr(d2), L.ptr(ws), wsb, L.stream()))
+    out = RadiusResult(idx, nrs, d2 if return_distances else torch.empty(0, device=dev))
+    return out if was_cuda else RadiusResult(*(t_.cpu() for t_ in out))
+
+
+class FixedRadiusSearch(torch.nn.Module):
+    """open3d.ml.torch.layers.FixedRadiusSearch (kpconv.py:2021-2026)."""
+
+    def __init__(self, metric="L2", ignore_query_point=False, return_distances=False,
+                 max_hash_table_size=32 * 2**20, index_dtype=torch.int32, **kwargs):
+        super().__init__()
+        if metric != "L2" or ignore_query_point:
+            raise RuntimeError("FixedRadiusSearch: only metric='L2', ignore_query_point=False")
+        self.return_distances = return_distances
+
+    def forward(self, points, queries, radius, points_row_splits=None, queries_row_splits=None,
+                hash_table_size_factor=1 / 64, hash_table=None):
+        return fixed_radius_search(points, queries, radius, points_row_splits, queries_row_splits,
+                                   self.return_distances)
+
+
+class KNNSearch(torch.nn.Module):
+    """open3d.ml.torch.layers.KNNSearch."""
+
+    def __init__(self, metric="L2", ignore_query_point=False, return_distances=False,
+                 index_dtype=torch.int32, **kwargs):
+        super().__init__()
+        self.kw = dict(metric=metric, ignore_query_point=ignore_query_point,
+                       return_distances=return_distances, index_dtype=index_dtype)
+
+    def forward(self, points, queries, k, points_row_splits=None, queries_row_splits=None):
+        return knn_search(points, queries, k, points_row_splits, queries_row_splits, **self.kw)
+
+
+class _O3CTensor:
+    """The sliver of open3d.core.Tensor that dataprocessing.py:99-103 touches."""
+
+    def __init__(self, t):
+        self.t = t
+
+    @staticmethod
+    def from_numpy(a):
+        return _O3CTensor(torch.from_numpy(np.ascontiguousarray(a)))
+
+    def numpy(self):
+        return self.t.cpu().numpy()
+
+
+class NearestNeighborSearch:
+    """open3d.core.nns.NearestNeighborSearch: knn_index(); knn_search(queries, k) -> (idx int64, d2)."""
+
+    def __init__(self, dataset_points, index_dtype=None):
+        t = dataset_points.t if isinstance(dataset_points, _O3CTensor) else torch.as_tensor(dataset_points)
+        self.points = _dev(t.to(torch.float32)).contiguous()
+
+    def knn_index(self):
+        return True
+
+    def knn_search(self, query_points, knn):
+        q = query_points.t if isinstance(query_points, _O3CTensor) else torch.as_tensor(query_points)
+        q = _dev(q.to(torch.float32)).contiguous()
+        r = knn_search(self.points, q, knn, index_dtype=torch.int64, return_distances=True)
+        n = q.shape[0]
+        return (_O3CTensor(r.neighbors_index.reshape(n, knn)),
+                _O3CTensor(r.neighbors_distance.reshape(n, knn)))

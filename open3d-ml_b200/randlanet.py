@@ -1,0 +1,204 @@
+"""RandLA-Net forward on the sm_100a kernels: the fused replacement of
+``RandLANet.forward`` (ml3d/torch/models/randlanet.py:241-298) and of the layers it
+calls (SharedMLP :471-518, LocalSpatialEncoding :521-605, AttentivePooling :608-639,
+LocalFeatureAggregation :642-692, random_sample :300-327, nearest_interpolation
+:329-350).
+
+The module is built from a reference ``state_dict`` (same keys as the model-zoo
+checkpoints), folds the eval-mode BatchNorms, and keeps every activation in
+point-major [B*N, C] float32 buffers.  Per LFA block:
+
+    linear(mlp1) -> lfa_pool(stage 1) -> linear(pool1.mlp) -> lfa_pool(stage 2)
+    -> linear(pool2.mlp) -> linear([p2 | feat] -> mlp2 + shortcut, LeakyReLU 0.01)
+    -> gather_max(random_sample)
+
+Inputs are exactly the reference's ``inputs`` dict (CPU or CUDA tensors, int64
+indices); the output is ``[B, N, num_classes]`` like the reference.
+"""
+import torch
+
+from . import _lib as L
+
+BN_EPS = 1e-6  # randlanet.py:77,499
+
+
+def _fold_bn(sd, prefix, bias=None, eps=BN_EPS):
+    s = sd[prefix + ".weight"].double() / torch.sqrt(sd[prefix + ".running_var"].double() + eps)
+    t = sd[prefix + ".bias"].double() - s * sd[prefix + ".running_mean"].double()
+    if bias is not None:
+        t = t + s * bias.double()
+    return s.float(), t.float()
+
+
+class RandLANetB200:
+    def __init__(self, state_dict, num_layers=4, num_neighbors=16, device=None):
+        L.require_cuda()
+        self.device = torch.device(device or "cuda")
+        self.num_layers = num_layers
+        self.k = num_neighbors
+        sd = {k: v.detach().to("cpu", torch.float32) if v.is_floating_point() else v.cpu()
+              for k, v in state_dict.items()}
+        self.w = {}
+        dev = self.device
+
+        def put(name, t):
+            self.w[name] = t.to(dev, torch.float32).contiguous()
+
+        def shared_mlp(p, transpose=False, bn=True):
+            w = sd[p + ".conv.weight"][:, :, 0, 0]
+            put(p + ".wt", w if transpose else w.t())
+            if bn:
+                s, t = _fold_bn(sd, p + ".batch_norm", sd[p + ".conv.bias"])
+                put(p + ".s", s)
+                put(p + ".t", t)
+            else:
+                put(p + ".t", sd[p + ".conv.bias"])
+
+        put("fc0.wt", sd["fc0.weight"].t())
+        s, t = _fold_bn(sd, "bn0", sd["fc0.bias"])
+        put("fc0.s", s), put("fc0.t", t)
+        self.d_out = []
+        for i in range(num_layers):
+            p = "encoder.%d" % i
+            shared_mlp(p + ".mlp1")
+            shared_mlp(p + ".lse1.mlp")
+            shared_mlp(p + ".lse2.mlp")
+            shared_mlp(p + ".pool1.mlp")
+            shared_mlp(p + ".pool2.mlp")
+            for pool in ("pool1", "pool2"):
+                put("%s.%s.score.wt" % (p, pool), sd["%s.%s.score_fn.0.weight" % (p, pool)].t())
+                put("%s.%s.score.b" % (p, pool), sd["%s.%s.score_fn.0.bias" % (p, pool)])
+            d = sd[p + ".pool2.mlp.conv.weight"].shape[0]
+            self.d_out.append(d)
+            # mlp2 + shortcut as ONE gemm over [p2 | feat] with the BN scales folded into the rows
+            s2, t2 = _fold_bn(sd, p + ".mlp2.batch_norm", sd[p + ".mlp2.conv.bias"])
+            ss, ts = _fold_bn(sd, p + ".shortcut.batch_norm", sd[p + ".shortcut.conv.bias"])
+            w2 = sd[p + ".mlp2.conv.weight"][:, :, 0, 0] * s2[:, None]
+            ws = sd[p + ".shortcut.conv.weight"][:, :, 0, 0] * ss[:, None]
+            put(p + ".out.wt", torch.cat([w2.t(), ws.t()], 0))
+            put(p + ".out.t", t2 + ts)
+        shared_mlp("mlp")
+        for i in range(num_layers):
+            shared_mlp("decoder.%d" % i, transpose=True)
+        shared_mlp("fc1.0")
+        shared_mlp("fc1.1")
+        shared_mlp("fc1.3", bn=False)
+        self.num_classes = sd["fc1.3.conv.weight"].shape[0]
+        self.in_channels = sd["fc0.weight"].shape[1]
+        self._buf = {}
+
+    # ------------------------------------------------------------------ buffers
+    def _get(self, name, rows, ch):
+        key = (name, rows, ch)
+        t = self._buf.get(key)
+        if t is None:
+            t = torch.empty((rows, ch), dtype=torch.float32, device=self.device)
+            self._buf[key] = t
+        return t
+
+    def _mlp(self, p, srcs, out, act="leaky", slope=0.2):
+        return L.linear(srcs, self.w[p + ".wt"], out, self.w.get(p + ".s"), self.w[p + ".t"],
+                        act=act, slope=slope)
+
+    def _lfa_pool(self, stage, d, coords, nidx, feat, B, N, p, agg):
+        w = self.w
+        pool = "pool1" if stage == 1 else "pool2"
+        L.check(L.lib().o3dml_randla_lfa_pool(
+            stage, d, L.ptr(coords), L.ptr(nidx), 1 if nidx.dtype == torch.int64 else 0, self.k,
+            L.ptr(feat), B, N, L.ptr(w[p + ".lse1.mlp.wt"]), L.ptr(w[p + ".lse1.mlp.s"]),
+            L.ptr(w[p + ".lse1.mlp.t"]),
+            L.ptr(w[p + ".lse2.mlp.wt"]) if stage == 2 else None,
+            L.ptr(w[p + ".lse2.mlp.s"]) if stage == 2 else None,
+            L.ptr(w[p + ".lse2.mlp.t"]) if stage == 2 else None,
+            L.ptr(w["%s.%s.score.wt" % (p, pool)]), L.ptr(w["%s.%s.score.b" % (p, pool)]),
+            L.ptr(agg), L.stream()))
+
+    # ------------------------------------------------------------------ forward
+    def to_device(self, inputs):
+        """The H2D step of RandLANet.forward (randlanet.py:254-264)."""
+        dev = self.device
+
+        def mv(t):
+            return t.to(dev, non_blocking=True).contiguous()
+        return dict(features=mv(inputs["features"]),
+                    coords=[mv(a) for a in inputs["coords"]],
+                    neighbor_indices=[mv(a) for a in inputs["neighbor_indices"]],
+                    sub_idx=[mv(a) for a in inputs["sub_idx"]],
+                    interp_idx=[mv(a) for a in inputs["interp_idx"]])
+
+    def forward(self, inputs, taps=None):
+        inp = self.to_device(inputs)
+        feats = inp["features"]
+        B, N0, cin = feats.shape
+        x = self._get("fc0", B * N0, self.w["fc0.wt"].shape[1])
+        L.linear([L.make_src(feats.view(B * N0, cin))], self.w["fc0.wt"], x, self.w["fc0.s"],
+                 self.w["fc0.t"], act="leaky", slope=0.2)
+        skips = []
+        for i in range(self.num_layers):
+            p = "encoder.%d" % i
+            d = self.d_out[i]
+            h = d // 2
+            coords = inp["coords"][i]
+            nidx = inp["neighbor_indices"][i]
+            N = coords.shape[1]
+            rows = B * N
+            cflat = coords.view(rows, 3)
+            f1 = self._mlp(p + ".mlp1", [L.make_src(x)], self._get(p + ".f1", rows, h))
+            agg1 = self._get(p + ".agg1", rows, d)
+            self._lfa_pool(1, d, cflat, nidx, f1, B, N, p, agg1)
+            p1 = self._mlp(p + ".pool1.mlp", [L.make_src(agg1)], self._get(p + ".p1", rows, h))
+            agg2 = self._get(p + ".agg2", rows, d)
+            self._lfa_pool(2, d, cflat, nidx, p1, B, N, p, agg2)
+            p2 = self._mlp(p + ".pool2.mlp", [L.make_src(agg2)], self._get(p + ".p2", rows, d))
+            enc = self._get(p + ".enc", rows, 2 * d)
+            L.linear([L.make_src(p2), L.make_src(x)], self.w[p + ".out.wt"], enc, None,
+                     self.w[p + ".out.t"], act="leaky", slope=0.01)
+            if taps is not None:
+                taps[p + ".pool1"] = p1.view(B, N, h)
+                taps[p] = enc.view(B, N, 2 * d)
+            sub = inp["sub_idx"][i]
+            ns = sub.shape[1]
+            pooled = self._get(p + ".sub", B * ns, 2 * d)
+            L.check(L.lib().o3dml_gather_max(L.ptr(enc), rows, 2 * d, 2 * d, L.ptr(sub),
+                                             1 if sub.dtype == torch.int64 else 0, B * ns,
+                                             sub.shape[2], ns, N, 0, L.ptr(pooled), 2 * d,
+                                             L.stream()))
+            if i == 0:
+                skips.append((enc, N))
+            skips.append((pooled, ns))
+            x = pooled
+        nlast = skips[-1][1]
+        x = self._mlp("mlp", [L.make_src(x)], self._get("mlp", x.shape[0], x.shape[1]))
+        ncoarse = nlast
+        for i in range(self.num_layers):
+            skip, nup = skips[-i - 2]
+            interp = inp["interp_idx"][-i - 1]  # [B, nup, 1] ids into the coarse level
+            p = "decoder.%d" % i
+            cout = self.w[p + ".wt"].shape[1]
+            out = self._get(p, B * nup, cout)
+            self._mlp(p, [L.make_src(skip),
+                          L.make_src(x, index=interp.view(-1), index_ld=1, out_rows_per_batch=nup,
+                                     src_rows_per_batch=ncoarse)], out)
+            if taps is not None:
+                taps[p] = out.view(B, nup, cout)
+            x, ncoarse = out, nup
+        y = self._mlp("fc1.0", [L.make_src(x)], self._get("fc1.0", x.shape[0], 64))
+        y = self._mlp("fc1.1", [L.make_src(y)], self._get("fc1.1", x.shape[0], 32))
+        logits = torch.empty((B * N0, self.num_classes), dtype=torch.float32, device=self.device)
+        self._mlp("fc1.3", [L.make_src(y)], logits, act=None)
+        return logits.view(B, N0, self.num_classes)
+
+    __call__ = forward
+
+
+def patch_reference_model(model):
+    """Drop-in: make an (unmodified) reference ``RandLANet`` instance run its forward on the
+    fused CUDA path (keeps preprocess/transform/losses).  BN must be in eval mode."""
+    fused = RandLANetB200(model.state_dict(), model.cfg.num_layers, model.cfg.num_neighbors)
+
+    def forward(inputs):
+        if model.training:
+            raise RuntimeError("open3d_ml_b200: the fused RandLA-Net path is inference-only")
+        return fused.forward(inputs)
+    model.forward = forward
+    return model
