@@ -1,0 +1,152 @@
+"""Model-level parity of the fused CUDA forwards:
+  (a) against the golden fixtures produced by the UNMODIFIED reference classes
+      (tests/golden/make_golden.py), weights rebuilt from (manifest, seed);
+  (b) against the torch port (oracle/models_torch.py) at the BASELINE.json sizes.
+Tolerance: 1e-4 relative to the tensor scale for float features/logits (north_star);
+indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import models_torch as MT, ops as O
+from open3d_ml_b200 import synth
+import open3d_ml_b200 as M
+from conftest import rel_err
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+# ------------------------------------------------------------------ RandLA-Net
+def test_randlanet_vs_golden_reference():
+    g = H.golden("randlanet_small.npz")
+    sd, _ = H.state_dict("randlanet_semantickitti.manifest.json", g["weight_seed"])
+    inp = H.randla_inputs(int(g["B"]), int(g["N"]), int(g["seed0"]))
+    net = M.RandLANetB200(sd)
+    taps = {}
+    out = net(inp, taps=taps)
+    for i in range(4):
+        assert rel_err(taps["encoder.%d.pool1" % i], g["tap.encoder.%d.pool1" % i]) < TOL, i
+        assert rel_err(taps["encoder.%d" % i], g["tap.encoder.%d" % i]) < TOL, i
+    assert out.shape == g["logits"].shape
+    assert rel_err(out, g["logits"]) < TOL
+    assert torch.equal(out.argmax(-1).cpu(), torch.from_numpy(g["logits"]).argmax(-1))
+
+
+def test_randlanet_full_size_vs_port_with_gpu_knn_pyramid():
+    """SemanticKITTI shape (45 056 pts), B=2; the KNN pyramid itself comes from the CUDA
+    knn_search (bit-exact to the oracle, test_gpu_ops.py), then the fused forward is compared
+    with the CPU port on identical inputs."""
+    def gpu_knn(s, q, k):
+        r = M.knn_search(torch.from_numpy(s).cuda(), torch.from_numpy(q).cuda(), k, index_dtype=torch.int64)
+        return r.neighbors_index.reshape(len(q), k).cpu().numpy()
+    sd, _ = H.state_dict("randlanet_semantickitti.manifest.json", 7)
+    inp = H.randla_inputs(2, 45056, 500, knn=gpu_knn)
+    ref_nb = O.c_knn(inp["coords"][1][0].numpy(), inp["coords"][1][0].numpy(), 16)[0]
+    assert np.array_equal(inp["neighbor_indices"][1][0].numpy(), ref_nb)
+    net = M.RandLANetB200(sd)
+    out = net(inp)
+    torch.set_num_threads(max(torch.get_num_threads(), 8))
+    with torch.no_grad():
+        ref = MT.randlanet_forward(sd, inp)
+    assert out.shape == (2, 45056, 19)
+    assert rel_err(out, ref) < TOL
+    out2 = net(inp)                                         # buffers are reused: idempotent
+    assert torch.equal(out, out2)
+
+
+def test_randlanet_accepts_cuda_inputs_and_int32_indices():
+    sd, _ = H.state_dict("randlanet_semantickitti.manifest.json", 3)
+    inp = H.randla_inputs(1, 1024, 40)
+    net = M.RandLANetB200(sd)
+    a = net(inp)
+    inp32 = {k: ([t.cuda().to(torch.int32) if t.dtype == torch.int64 else t.cuda() for t in v]
+                 if isinstance(v, list) else v.cuda()) for k, v in inp.items()}
+    assert torch.equal(a, net(inp32))
+
+
+# ---------------------------------------------------------------- PointPillars
+def test_pointpillars_vs_golden_reference_kitti():
+    g = H.golden("pointpillars_kitti.npz")
+    sd, extra = H.state_dict("pointpillars_kitti.manifest.json", g["weight_seed"])
+    frames = [torch.from_numpy(synth.lidar_frame(int(g["frame_sizes"][0]), int(g["frame_seeds"][0]))),
+              torch.from_numpy(synth.uniform_frame(int(g["frame_sizes"][1]), int(g["frame_seeds"][1])))]
+    net = M.PointPillarsB200(sd, extra["cfg"])
+    canvas, vox = net.front_end(frames, want_feat=True)
+    m = int(vox["counts"][0])
+    # index-level parity with the reference's voxelize + post-processing (z,y,x order, batch id first)
+    co = torch.cat([vox["batch_id"][:m, None], vox["coords"][:m][:, [2, 1, 0]]], 1).cpu().numpy()
+    cnt = (vox["row_splits"][1:m + 1] - vox["row_splits"][:m]).cpu().numpy()
+    keep = (co[:, 2] < 496) & (co[:, 3] < 432)
+    assert np.array_equal(co[keep], g["coords"]) and np.array_equal(cnt[keep], g["counts"])
+    feat = vox["feat"][:m][torch.from_numpy(keep).cuda()]
+    assert rel_err(feat[torch.from_numpy(g["pfn_rows"]).cuda()], g["pfn_vals"]) < TOL
+    assert abs(canvas.double().sum().item() - float(g["canvas_sum"])) < 1e-5 * float(g["canvas_abs_sum"])
+    outs = net.backbone_neck_head(canvas)
+    for name, o in zip(("cls", "reg", "dir"), outs):
+        assert tuple(o.shape) == tuple(g[name + "_shape"])
+        assert rel_err(o.reshape(-1)[torch.from_numpy(g[name + "_idx"]).cuda()], g[name + "_vals"]) < TOL, name
+
+
+def test_pointpillars_small_full_tensors_and_nchw_canvas():
+    g = H.golden("pointpillars_small.npz")
+    sd, extra = H.state_dict("pointpillars_kitti.manifest.json", g["weight_seed"])
+    cfg = dict(extra["cfg"], point_cloud_range=[0, -10.24, -3, 20.48, 10.24, 1], output_shape=[128, 128])
+    f = [torch.from_numpy(synth.lidar_frame(int(g["frame_size"]), int(g["frame_seed"]), tuple(cfg["point_cloud_range"])))]
+    net = M.PointPillarsB200(sd, cfg)
+    outs = net(f)
+    for name, o in zip(("cls", "reg", "dir"), outs):
+        assert rel_err(o, g[name]) < TOL, name
+    nhwc = net.front_end(f)[0].clone()
+    nchw = net.front_end(f, canvas_nchw=True)[0]            # layout of PointPillarsScatter.forward
+    assert torch.equal(nchw, nhwc.permute(0, 3, 1, 2))
+    taps = {}
+    with torch.no_grad():
+        MT.pointpillars_forward(sd, f, cfg, taps=taps)
+    assert rel_err(nchw, taps["canvas"]) < TOL
+
+
+def test_pointpillars_waymo_shape_vs_port():
+    sd, extra = H.state_dict("pointpillars_waymo.manifest.json", 11)
+    frames = [torch.from_numpy(synth.lidar_frame(60000, 30 + i, synth.WAYMO_RANGE)) for i in range(2)]
+    net = M.PointPillarsB200(sd, extra["cfg"])
+    outs = net(frames)
+    with torch.no_grad():
+        ref = MT.pointpillars_forward(sd, frames, extra["cfg"])
+    for o, r in zip(outs, ref):
+        assert o.shape == r.shape and rel_err(o, r) < TOL
+
+
+# --------------------------------------------------------------------- KPConv
+def test_kpfcnn_vs_golden_reference():
+    g = H.golden("kpconv_small.npz")
+    sd, extra = H.state_dict("kpconv_s3dis.manifest.json", g["weight_seed"])
+    clouds = [synth.room_cloud(int(n), int(s), room=H.KP_SMALL_ROOM) for n, s in zip(g["cloud_sizes"], g["cloud_seeds"])]
+    bd = H.kp_batch(clouds, extra["cfg"])
+    net = M.KPFCNNB200(sd, extra["cfg"])
+    taps = {}
+    out = net(H.kp_batch_tensors(bd), taps=taps)
+    for k in ("encoder_blocks.0", "encoder_blocks.1", "encoder_blocks.2", "encoder_blocks.12"):
+        assert rel_err(taps[k][torch.from_numpy(g["tap.%s.rows" % k]).cuda()], g["tap." + k]) < TOL, k
+    assert rel_err(out, g["logits"]) < TOL
+
+
+def test_kpfcnn_medium_vs_port_with_gpu_radius_pyramid():
+    """20 000-pt room cloud; the 13 radius searches of KPConvBatch (concat_batcher.py:186-305)
+    run on the GPU (bit-exact to the oracle), the fused forward is compared with the port."""
+    def gpu_radius(supports, queries, radius, ss, qs):
+        r = M.fixed_radius_search(torch.from_numpy(supports).cuda(), torch.from_numpy(queries).cuda(), radius,
+                                  torch.from_numpy(ss).cuda(), torch.from_numpy(qs).cuda())
+        return r.neighbors_index.cpu().numpy(), r.neighbors_row_splits.cpu().numpy(), None
+    sd, extra = H.state_dict("kpconv_s3dis.manifest.json", 5)
+    clouds = [synth.room_cloud(12000, 70, room=(3.0, 2.5, 2.0)), synth.room_cloud(8000, 71, room=(3.0, 2.5, 2.0))]
+    bd = H.kp_batch(clouds, extra["cfg"], radius_search=gpu_radius)
+    ref_nb = MT.kp_batch_neighbors(bd["points"][1], bd["points"][1], bd["lengths"][1], bd["lengths"][1], 0.2)
+    assert np.array_equal(bd["neighbors"][1], ref_nb)
+    net = M.KPFCNNB200(sd, extra["cfg"])
+    tb = H.kp_batch_tensors(bd)
+    out = net(tb)
+    with torch.no_grad():
+        ref = MT.kpfcnn_forward(sd, tb, extra["cfg"])
+    assert out.shape == ref.shape and rel_err(out, ref) < TOL

@@ -1,0 +1,197 @@
+"""Parity of the CUDA operators (through the C ABI) against the CPU oracle: bit-exact
+for voxel / neighbour indices and squared distances."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops as O
+from open3d_ml_b200 import synth
+import open3d_ml_b200 as M
+
+pytestmark = pytest.mark.gpu
+KITTI = dict(voxel_size=[0.16, 0.16, 4], rmin=[0, -39.68, -3], rmax=[69.12, 39.68, 1])
+WAYMO = dict(voxel_size=[0.32, 0.32, 6], rmin=[-74.88, -74.88, -2], rmax=[74.88, 74.88, 4])
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def vox_check(pts, splits, g, max_pts, max_vox):
+    ref = O.c_voxelize(pts[:, :3], splits, g["voxel_size"], g["rmin"], g["rmax"], max_pts, max_vox)
+    rs = None if splits is None else T(np.asarray(splits, np.int64))
+    out = M.voxelize(T(pts)[:, :3], rs if rs is not None else torch.tensor([0, len(pts)]).cuda(),
+                     torch.tensor(g["voxel_size"]), torch.tensor(g["rmin"], dtype=torch.float32),
+                     torch.tensor(g["rmax"], dtype=torch.float32), max_pts, max_vox)
+    assert out.voxel_coords.dtype == torch.int32 and out.voxel_point_indices.dtype == torch.int64
+    assert np.array_equal(out.voxel_coords.cpu().numpy(), ref["voxel_coords"])
+    assert np.array_equal(out.voxel_point_row_splits.cpu().numpy(), ref["voxel_point_row_splits"])
+    assert np.array_equal(out.voxel_point_indices.cpu().numpy(), ref["voxel_point_indices"])
+    assert np.array_equal(out.voxel_batch_splits.cpu().numpy(), ref["voxel_batch_splits"])
+    return ref
+
+
+def test_voxelize_kitti_lidar_and_uniform():
+    pts = synth.lidar_frame(20000, 3)
+    pts[:7, 0] = 69.12           # p == max: kept, index == extent
+    pts[7:11, 1] = 39.68
+    pts[11:20, 2] = 5.0          # out of range
+    pts[20:24, 0] = np.nan
+    ref = vox_check(pts, None, KITTI, 32, 40000)
+    assert ref["voxel_coords"][:, 0].max() == 432 and ref["voxel_coords"][:, 1].max() == 496
+    vox_check(synth.uniform_frame(20000, 4), None, KITTI, 32, 40000)
+    vox_check(synth.uniform_frame(20000, 4), None, KITTI, 32, 16000)     # max_voxels cap active
+
+
+def test_voxelize_caps_reference_smoke_shape():
+    rng = np.random.default_rng(0)      # tests/test_models.py:204-236: 10 000 pts in [0,1)^4
+    pts = rng.uniform(0, 1, (10000, 4)).astype(np.float32)
+    ref = vox_check(pts, None, KITTI, 32, 40000)
+    assert np.diff(ref["voxel_point_row_splits"]).max() == 32
+    vox_check(pts, None, KITTI, 5, 7)
+
+
+def test_voxelize_batched_ragged_empty():
+    frames = [synth.lidar_frame(n, 10 + i) for i, n in enumerate((5000, 0, 12345, 1))]
+    pts = np.concatenate(frames)
+    splits = np.concatenate([[0], np.cumsum([len(f) for f in frames])])
+    vox_check(pts, splits, KITTI, 32, 3000)
+    vox_check(pts, splits, KITTI, 4, 40000)
+    out = M.voxelize(torch.zeros((0, 3)).cuda(), torch.tensor([0, 0]).cuda(), torch.tensor([1., 1, 1]),
+                     torch.zeros(3), torch.ones(3), 4, 4)
+    assert out.voxel_coords.shape == (0, 3) and out.voxel_point_row_splits.tolist() == [0]
+
+
+def test_voxelize_waymo_full_size_and_3d_grid():
+    vox_check(synth.lidar_frame(180000, 5, synth.WAYMO_RANGE), None, WAYMO, 20, 32000)
+    g3 = dict(voxel_size=[0.5, 0.4, 0.3], rmin=[-50, -50, -3], rmax=[50, 50, 1])   # many z cells
+    vox_check(synth.semantickitti_cloud(45056, 6), None, g3, 3, 100000)
+
+
+def test_voxelize_is_deterministic_and_validates():
+    pts = T(synth.uniform_frame(30000, 8))
+    args = (torch.tensor([0, 30000]).cuda(), torch.tensor(KITTI["voxel_size"]),
+            torch.tensor(KITTI["rmin"], dtype=torch.float32), torch.tensor(KITTI["rmax"], dtype=torch.float32), 32, 40000)
+    a, b = M.voxelize(pts[:, :3], *args), M.voxelize(pts[:, :3], *args)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    with pytest.raises(RuntimeError):
+        M.voxelize(pts[:, :2], *args)
+    with pytest.raises(RuntimeError):
+        M.voxelize(pts[:, :3], args[0], torch.tensor([0., 1, 1]), *args[2:])
+
+
+def test_ragged_to_dense():
+    rng = np.random.default_rng(1)
+    lens = rng.integers(0, 40, 500)
+    rs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    v64 = rng.integers(0, 10**9, rs[-1]).astype(np.int64)
+    out = M.ragged_to_dense(T(v64), T(rs), 32, torch.tensor(-1))
+    assert np.array_equal(out.cpu().numpy(), O.np_ragged_to_dense(v64, rs, 32, -1))
+    v32 = v64.astype(np.int32).reshape(-1, 1)          # kpconv.py:2030-2032 form: [L,1], int32 fill tensor
+    out = M.ragged_to_dense(T(v32), T(rs), 36, torch.Tensor([12345]).to(torch.int32))
+    assert out.shape == (500, 36, 1)
+    assert np.array_equal(out.cpu().numpy(), O.np_ragged_to_dense(v32, rs, 36, np.int32(12345)))
+    out = M.ragged_to_dense(torch.from_numpy(v64), torch.from_numpy(rs), 8, torch.tensor(-1))   # CPU in -> CPU out
+    assert not out.is_cuda and np.array_equal(out.numpy(), O.np_ragged_to_dense(v64, rs, 8, -1))
+
+
+def knn_check(P, Q, k, ps=None, qs=None, dtype=torch.int32):
+    ri, rd = O.c_knn(P, Q, k, ps, qs)
+    r = M.knn_search(T(P), T(Q), k, None if ps is None else T(np.asarray(ps, np.int64)),
+                     None if qs is None else T(np.asarray(qs, np.int64)), index_dtype=dtype,
+                     return_distances=True)
+    gi = r.neighbors_index.reshape(len(Q), k).cpu().numpy()
+    gd = r.neighbors_distance.reshape(len(Q), k).cpu().numpy()
+    assert gi.dtype == (np.int32 if dtype == torch.int32 else np.int64)
+    assert np.array_equal(gi.astype(np.int64), ri.astype(np.int64)), "index mismatch in %d rows" % (gi != ri).any(1).sum()
+    assert np.array_equal(gd, rd)
+    return gi
+
+
+def test_knn_small_uniform_lidar_and_cross():
+    P = synth.uniform_cloud(4096, 1)                       # BASELINE config 1 shape
+    knn_check(P, P, 16)
+    knn_check(P[:1024], P, 1, dtype=torch.int64)           # interp_idx (randlanet.py:224)
+    L_ = synth.semantickitti_cloud(8192, 2)
+    knn_check(L_, L_, 16)
+    knn_check(L_, synth.uniform_cloud(3000, 3, -60, 60), 5)    # queries far outside the support bbox
+    knn_check(L_, L_[:100], 33)
+    knn_check(L_[:2000], L_[:50], 64)
+
+
+def test_knn_batched_short_items_and_duplicates():
+    P = synth.uniform_cloud(3000, 4)
+    P[100:110] = P[0]
+    Q = synth.uniform_cloud(700, 5)
+    gi = knn_check(P, Q, 8, [0, 2000, 2005, 3000], [0, 300, 350, 700])
+    assert (gi[300:350, 5:] == -1).all()
+    knn_check(P[:2000], P[:200], 12)
+    flat = synth.uniform_cloud(5000, 6)
+    flat[:, 2] = 0.25                                    # degenerate (planar) extent
+    knn_check(flat, flat, 16)
+    same = np.repeat(synth.uniform_cloud(1, 7), 200, 0)  # all points identical: pure index order
+    assert np.array_equal(knn_check(same, same, 16), np.tile(np.arange(16), (200, 1)))
+
+
+def test_knn_randla_pyramid_full_size():
+    """SemanticKITTI-shaped cloud, all four levels (randlanet.py:218-229), vs brute force."""
+    pc = synth.semantickitti_cloud(45056, 11)
+    for _ in range(4):
+        gi = knn_check(pc, pc, 16)
+        assert np.array_equal(gi[:, 0], np.arange(len(pc)))
+        sub = pc[:len(pc) // 4]
+        knn_check(sub, pc, 1, dtype=torch.int64)
+        pc = sub
+
+
+def test_nearest_neighbor_search_object_numpy_path():
+    P = synth.uniform_cloud(2000, 8)
+    nns = M.NearestNeighborSearch(M.ops._O3CTensor.from_numpy(P))
+    nns.knn_index()
+    idx, d = nns.knn_search(M.ops._O3CTensor.from_numpy(P[:500]), 16)
+    ri, rd = O.c_knn(P, P[:500], 16)
+    assert idx.numpy().dtype == np.int64 and np.array_equal(idx.numpy(), ri) and np.array_equal(d.numpy(), rd)
+
+
+def radius_check(P, Q, r, ps=None, qs=None):
+    ri, rrs, rd = O.c_radius(P, Q, r, ps, qs)
+    out = M.fixed_radius_search(T(P), T(Q), r, None if ps is None else T(np.asarray(ps, np.int64)),
+                                None if qs is None else T(np.asarray(qs, np.int64)))
+    assert out.neighbors_index.dtype == torch.int32 and out.neighbors_row_splits.dtype == torch.int64
+    assert np.array_equal(out.neighbors_row_splits.cpu().numpy(), rrs)
+    assert np.array_equal(out.neighbors_index.cpu().numpy(), ri)
+    assert np.array_equal(out.neighbors_distance.cpu().numpy(), rd)
+    return rrs
+
+
+def test_radius_search_room_pyramid_radii():
+    P, _ = synth.room_cloud(20000, 5)
+    for dl, r in ((0.04, 0.1), (0.08, 0.2), (0.16, 0.4)):
+        S = P if dl == 0.04 else synth.grid_subsample(P, dl)
+        radius_check(S, S, r)                                # conv neighbours
+        Q = synth.grid_subsample(S, 2 * dl)
+        radius_check(S, Q, r)                                # pool
+        radius_check(Q, S, 2 * r)                            # upsample
+
+
+def test_radius_search_batched_empty_and_layer_api():
+    P = synth.uniform_cloud(3000, 9, 0, 4)
+    Q = synth.uniform_cloud(500, 10, -1, 5)                  # some queries have no neighbour at all
+    rrs = radius_check(P, Q, 0.3, [0, 0, 1200, 3000], [0, 40, 300, 500])
+    assert (rrs[:41] == 0).all() and (np.diff(rrs) == 0).any()
+    nns = M.FixedRadiusSearch()                              # kpconv.py:2021-2026, CPU tensors in/out
+    res = nns(torch.from_numpy(P), torch.from_numpy(Q), 0.3, torch.tensor([0, 3000]), torch.tensor([0, 500]))
+    ri, rs_, _ = O.c_radius(P, Q, 0.3)
+    assert not res.neighbors_index.is_cuda and np.array_equal(res.neighbors_index.numpy(), ri)
+    assert np.array_equal(res.neighbors_row_splits.numpy(), rs_)
+    with pytest.raises(RuntimeError):
+        M.fixed_radius_search(T(P), T(Q), -1.0)
+
+
+def test_search_is_deterministic():
+    P = T(synth.semantickitti_cloud(20000, 12))
+    a = M.knn_search(P, P, 16, return_distances=True)
+    b = M.knn_search(P, P, 16, return_distances=True)
+    assert torch.equal(a.neighbors_index, b.neighbors_index) and torch.equal(a.neighbors_distance, b.neighbors_distance)
+    c, d = M.fixed_radius_search(P, P, 0.5), M.fixed_radius_search(P, P, 0.5)
+    assert torch.equal(c.neighbors_index, d.neighbors_index) and torch.equal(c.neighbors_row_splits, d.neighbors_row_splits)

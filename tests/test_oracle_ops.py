@@ -1,0 +1,123 @@
+"""The op oracle pinned against itself (C brute force vs numpy/KD-tree), against
+scipy / sklearn KD-trees, and against hand-computable cases (parity is otherwise
+UNPINNED by the reference: SURVEY.md 8c)."""
+import numpy as np
+import pytest
+
+from oracle import ops as O
+from open3d_ml_b200 import synth
+
+KITTI = dict(voxel_size=[0.16, 0.16, 4], range_min=[0, -39.68, -3], range_max=[69.12, 39.68, 1])
+
+
+def test_voxelize_c_vs_numpy_and_invariants():
+    pts = synth.lidar_frame(20000, 3)[:, :3]
+    pts[:7, 0] = 69.12      # p == max is kept and yields index == extent
+    pts[7:11, 1] = 39.68
+    pts[11:20, 2] = 5.0     # out of range
+    a = O.c_voxelize(pts, None, KITTI["voxel_size"], KITTI["range_min"], KITTI["range_max"], 32, 40000)
+    b = O.np_voxelize(pts, None, KITTI["voxel_size"], KITTI["range_min"], KITTI["range_max"], 32, 40000)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    c, rs, pi = a["voxel_coords"], a["voxel_point_row_splits"], a["voxel_point_indices"]
+    assert c[:, 0].max() == 432 and c[:, 1].max() == 496
+    lin = c[:, 0].astype(np.int64) + 1000 * (c[:, 1] + 1000 * c[:, 2].astype(np.int64))
+    assert np.all(np.diff(lin) > 0)                      # voxels ascend, unique
+    assert np.all(np.diff(rs) >= 1) and np.all(np.diff(rs) <= 32)
+    for v in range(0, len(rs) - 1, 97):
+        ids = pi[rs[v]:rs[v + 1]]
+        assert np.all(np.diff(ids) > 0)                  # ids ascend inside a voxel
+        ijk = ((pts[ids] - np.float32(KITTI["range_min"])) * (np.float32(1) / np.float32(KITTI["voxel_size"]))).astype(np.int64)
+        assert np.all(ijk == c[v])
+    assert not np.isin(np.arange(11, 20), pi).any()
+
+
+def test_voxelize_caps_and_batch():
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(0, 1, (10000, 3)).astype(np.float32)   # reference smoke test shape (test_models.py:204-236)
+    a = O.c_voxelize(pts, [0, 4000, 4000, 10000], [0.16, 0.16, 4], [0, -39.68, -3], [69.12, 39.68, 1], 32, 20)
+    b = O.np_voxelize(pts, [0, 4000, 4000, 10000], [0.16, 0.16, 4], [0, -39.68, -3], [69.12, 39.68, 1], 32, 20)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert list(a["voxel_batch_splits"]) == [0, 20, 20, 40]
+    assert np.diff(a["voxel_point_row_splits"]).max() == 32
+    # first 32 ids of the first voxel of batch 0 are the 32 smallest ids in that cell
+    cell0 = a["voxel_coords"][0]
+    ijk = (pts[:4000] * (np.float32(1) / np.float32([0.16, 0.16, 4]))).astype(np.int64)
+    ijk[:, 1] = ((pts[:4000, 1] + np.float32(39.68)) * (np.float32(1) / np.float32(0.16))).astype(np.int64)
+    ijk[:, 2] = ((pts[:4000, 2] + np.float32(3)) * np.float32(0.25)).astype(np.int64)
+    members = np.nonzero(np.all(ijk == cell0, axis=1))[0]
+    assert np.array_equal(a["voxel_point_indices"][:32], members[:32])
+
+
+def test_voxelize_empty():
+    a = O.c_voxelize(np.zeros((0, 3), np.float32), None, [1, 1, 1], [0, 0, 0], [4, 4, 4])
+    assert a["voxel_coords"].shape == (0, 3) and list(a["voxel_point_row_splits"]) == [0]
+
+
+def test_ragged_to_dense():
+    v = np.arange(10, dtype=np.int64)
+    out = O.np_ragged_to_dense(v, [0, 3, 3, 10], 4, -1)
+    assert out.tolist() == [[0, 1, 2, -1], [-1, -1, -1, -1], [3, 4, 5, 6]]
+
+
+@pytest.mark.parametrize("gen", ["uniform", "lidar"])
+def test_knn_c_vs_numpy_vs_kdtree(gen):
+    from scipy.spatial import cKDTree
+    from sklearn.neighbors import KDTree
+    P = synth.uniform_cloud(6000, 1) if gen == "uniform" else synth.semantickitti_cloud(6000, 1)
+    i1, d1 = O.c_knn(P, P, 16)
+    i2, d2 = O.np_knn(P, P, 16)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    assert np.array_equal(i1[:, 0], np.arange(len(P)))            # self first
+    assert np.all(np.diff(d1, axis=1) >= 0)
+    dk, ik = cKDTree(P).query(P, 16)
+    assert np.array_equal(ik, i1)                                   # tie-free input: exact index parity
+    np.testing.assert_allclose(np.sqrt(d1), dk, rtol=1e-5, atol=1e-6)
+    isk = KDTree(P).query(P[:500], 16, return_distance=False)
+    assert np.array_equal(isk, i1[:500])
+    # cross-set k=1 (interp_idx of randlanet.py:224)
+    sub = P[:1500]
+    j1, _ = O.c_knn(sub, P, 1)
+    assert np.array_equal(j1[:, 0], cKDTree(sub).query(P, 1)[1])
+
+
+def test_knn_batched_short_and_ties():
+    P = synth.uniform_cloud(300, 2)
+    P[100:110] = P[0]                      # duplicates: ties resolved by index
+    ps, qs = [0, 200, 205, 300], [0, 50, 60, 100]
+    Q = synth.uniform_cloud(100, 3)
+    i1, d1 = O.c_knn(P, Q, 8, ps, qs)
+    i2, d2 = O.np_knn(P, Q, 8, ps, qs)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    assert np.all(i1[50:60, 5:] == -1) and np.all(np.isinf(d1[50:60, 5:]))   # batch item with 5 points
+    assert i1[:50].max() < 200 and i1[60:].min() >= 205
+    i3, _ = O.c_knn(P[:200], P[:1], 12)
+    assert list(i3[0, :11]) == [0] + list(range(100, 110))
+
+
+def test_radius_c_vs_numpy_vs_kdtree():
+    from scipy.spatial import cKDTree
+    P, _ = synth.room_cloud(5000, 5, room=(2.0, 1.6, 1.2))
+    Q = P[::3]
+    i1, r1, d1 = O.c_radius(P, Q, 0.1)
+    i2, r2, d2 = O.np_radius(P, Q, 0.1)
+    assert np.array_equal(r1, r2) and np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    # points on a 0.04 grid put many pairs EXACTLY at radius-like distances; compare to the
+    # float64 KD-tree on a radius that is not a lattice distance
+    i3, r3, _ = O.c_radius(P, Q, 0.107)
+    ball = cKDTree(P).query_ball_point(Q.astype(np.float64), 0.107)
+    for q in range(0, len(Q), 37):
+        assert sorted(ball[q]) == sorted(i3[r3[q]:r3[q + 1]].tolist())
+    # rows ascend by (d2, idx)
+    for q in range(0, len(Q), 53):
+        row = list(zip(d1[r1[q]:r1[q + 1]].tolist(), i1[r1[q]:r1[q + 1]].tolist()))
+        assert row == sorted(row)
+
+
+def test_radius_batched_empty():
+    P = synth.uniform_cloud(400, 4)
+    i1, r1, _ = O.c_radius(P, P[:50], 0.9, [0, 0, 400], [0, 10, 50])
+    i2, r2, _ = O.np_radius(P, P[:50], 0.9, [0, 0, 400], [0, 10, 50])
+    assert np.array_equal(r1, r2) and np.array_equal(i1, i2)
+    assert np.all(r1[:11] == 0)             # first batch item has no support points
