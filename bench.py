@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py -- forward throughput (M points/s) of the hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload randlanet|pointpillars|kpconv]
+    python bench.py --impl reference ...        # the CPU arm (torch port of the reference forward)
+
+Launched by the driver either directly (N = 1) or through torch.distributed.run (one rank
+per GPU, NCCL).  One JSON line on rank 0.  A "step" is one forward pass of the workload's
+model over one synthetic batch:
+
+  randlanet    (default; BASELINE.json configs[2]) RandLA-Net, SemanticKITTI shape:
+               8 clouds x 45 056 pts per GPU (frames shard across ranks: weak scaling)
+  pointpillars (configs[1]) PointPillars, KITTI shape: frames of ~20 000 pts
+  kpconv       (configs[3]) KPFCNN, S3DIS shape: clouds of 65 536 pts (rooms pre-gridded at 4 cm)
+
+`value` : inputs resident in HBM, K steps between two barrier+synchronize brackets, CUDA
+          events, max over ranks.
+`e2e`   : the same K steps through the public model call with PINNED HOST inputs: H2D of every
+          input tensor and D2H of the logits inside the timed region.
+`roofline`: the dominant kernel class, timed with CUDA events inside the timed steps.
+`cpu_baseline`: oracle/models_torch.py (the pinned port of the reference forward) on the
+          host cores, bounded sample (rank 0, N = 1 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+L2_BYTES = 126e6
+
+
+# ----------------------------------------------------------------------------- utilities
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (rank 0)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) == 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) == 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) == 6
+                          for n, v in zip(names, r[2:]) if v.lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+def pin(t):
+    return t.contiguous().pin_memory()
+
+
+def nbytes(x):
+    if isinstance(x, torch.Tensor):
+        return x.numel() * x.element_size()
+    if isinstance(x, dict):
+        return sum(nbytes(v) for v in x.values())
+    if isinstance(x, (list, tuple)):
+        return sum(nbytes(v) for v in x)
+    return 0
+
+
+def to_dev(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(dev, non_blocking=True)
+    if isinstance(x, dict):
+        return {k: to_dev(v, dev) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [to_dev(v, dev) for v in x]
+    return x
+
+
+# ----------------------------------------------------------------------------- workloads
+class RandLAWorkload:
+    name = "RandLA-Net forward, SemanticKITTI-shaped batch (8 x 45 056 pts per GPU), BASELINE configs[2]"
+    short = "randlanet_semantickitti_8x45056"
+    manifest = "randlanet_semantickitti.manifest.json"
+
+    def __init__(self, clouds=8, n=45056):
+        self.B, self.N = clouds, n
+
+    def points_per_step(self):
+        return self.B * self.N
+
+    def build_inputs_gpu(self, rank):
+        """KNN pyramid on the GPU (o3dml_knn_search), returned as HOST pinned tensors."""
+        import open3d_ml_b200 as M
+        from open3d_ml_b200 import synth
+        per = []
+        for b in range(self.B):
+            pc = torch.from_numpy(synth.semantickitti_cloud(self.N, 1000 * rank + b)).cuda()
+            lv = dict(coords=[], neighbor_indices=[], sub_idx=[], interp_idx=[])
+            for i in range(4):
+                n = pc.shape[0]
+                nb = M.knn_search(pc, pc, 16, index_dtype=torch.int64).neighbors_index.view(n, 16)
+                sub = pc[:n // 4]
+                up = M.knn_search(sub, pc, 1, index_dtype=torch.int64).neighbors_index.view(n, 1)
+                lv["coords"].append(pc)
+                lv["neighbor_indices"].append(nb)
+                lv["sub_idx"].append(nb[:n // 4])
+                lv["interp_idx"].append(up)
+                pc = sub
+            per.append(lv)
+        inp = {k: [pin(torch.stack([p[k][i] for p in per]).cpu()) for i in range(4)]
+               for k in ("coords", "neighbor_indices", "sub_idx", "interp_idx")}
+        inp["features"] = pin(inp["coords"][0].clone())
+        return inp
+
+    def build_inputs_cpu(self, clouds):
+        from oracle import models_torch as MT
+        from open3d_ml_b200 import synth
+        per = [MT.randlanet_build_inputs(synth.semantickitti_cloud(self.N, b)) for b in range(clouds)]
+        inp = {k: [torch.from_numpy(np.stack([p[k][i] for p in per])) for i in range(4)]
+               for k in ("coords", "neighbor_indices", "sub_idx", "interp_idx")}
+        inp["features"] = inp["coords"][0].clone()
+        return inp
+
+    def make_model(self, sd):
+        import open3d_ml_b200 as M
+        return M.RandLANetB200(sd)
+
+    def cpu_forward(self, sd, inp):
+        from oracle import models_torch as MT
+        return MT.randlanet_forward(sd, inp)
+
+    # algorithmic bytes of one lfa_pool launch: per point 12 (xyz) + 8*16 (idx)
+    # + 4*d/2 (gathered features, each input row once) + 4*d (pooled output)
+    def roofline_bytes(self, d, points):
+        return points * (12 + 128 + 2 * d + 4 * d)
+
+    def roofline_flops(self, d, stage, points):
+        h = d // 2
+        per_nk = 2 * d * d + 2 * 10 * h + (2 * h * h if stage == 2 else 0) + 3 * d
+        return points * 16 * per_nk
+
+
+class PointPillarsWorkload:
+    name = "PointPillars forward, synthetic KITTI frames (~20 000 pts), BASELINE configs[1]"
+    short = "pointpillars_kitti"
+    manifest = "pointpillars_kitti.manifest.json"
+
+    def __init__(self, frames=1, n=20000):
+        self.B, self.N = frames, n
+
+    def points_per_step(self):
+        return self.B * self.N
+
+    def build_inputs_gpu(self, rank):
+        from open3d_ml_b200 import synth
+        return [pin(torch.from_numpy(synth.lidar_frame(self.N, 1000 * rank + b))) for b in range(self.B)]
+
+    def build_inputs_cpu(self, frames):
+        from open3d_ml_b200 import synth
+        return [torch.from_numpy(synth.lidar_frame(self.N, b)) for b in range(frames)]
+
+    def make_model(self, sd):
+        import open3d_ml_b200 as M
+        return M.PointPillarsB200(sd, self.cfg)
+
+    def cpu_forward(self, sd, inp):
+        from oracle import models_torch as MT
+        return MT.pointpillars_forward(sd, inp, self.cfg)
+
+
+def load_weights(wl, seed=1):
+    from oracle import weights
+    man, extra = weights.load_manifest(os.path.join(ROOT, "tests", "golden", wl.manifest))
+    wl.cfg = extra.get("cfg")
+    return weights.seeded_state_dict(man, seed)
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args, wl):
+    """The reference's own forward on the host cores: the torch port of oracle/models_torch.py
+    (pinned to the unmodified reference classes by tests/test_oracle_models.py).  The reference
+    tree itself cannot be installed on the GPU box (its ops live in the absent `open3d` package,
+    SURVEY.md section 0), hence kind = "port"."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    sd = load_weights(wl)
+    sample = 1
+    inp = wl.build_inputs_cpu(sample)
+    pts = sample * wl.N
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            wl.cpu_forward(sd, inp)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            wl.cpu_forward(sd, inp)
+        dt = time.perf_counter() - t0
+    v = pts * args.steps / dt / 1e6
+    line = dict(metric="M points/s forward", value=round(v, 5), unit="Mpoints/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=round(1e3 * dt / args.steps, 3),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference",
+                config=dict(workload=wl.name, sample="%d unit(s) of %d pts per step" % (sample, wl.N)),
+                cpu_baseline=dict(value=round(v, 5), unit="Mpoints/s", cores=torch.get_num_threads(),
+                                  kind="port", sample="%d x %d pts, %d steps" % (sample, wl.N, args.steps)),
+                e2e=dict(value=round(v, 5), unit="Mpoints/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def timed_region(fn, steps, dist_on, dev):
+    import torch.distributed as dist
+    torch.cuda.synchronize(dev)
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if dist_on:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist_on:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def run_b200(args, wl):
+    import torch.distributed as dist
+    from open3d_ml_b200 import _lib as L
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist_on = world > 1
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    sd = load_weights(wl)
+    model = wl.make_model(sd)
+    host_inp = wl.build_inputs_gpu(rank)
+    dev_inp = to_dev(host_inp, dev)
+    out_host = None
+
+    def step_resident():
+        return model(dev_inp)
+
+    def step_e2e():
+        nonlocal out_host
+        out = model(host_inp)          # H2D of every input inside the model call (randlanet.py:254-264)
+        outs = out if isinstance(out, (tuple, list)) else (out,)
+        if out_host is None:
+            out_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+        for h, o in zip(out_host, outs):
+            h.copy_(o, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller consumes the result every step
+
+    for _ in range(args.warmup):
+        step_resident()
+    # --- roofline instrumentation: CUDA events around every launch of the dominant kernel class
+    timers = []
+    if hasattr(model, "_lfa_pool"):
+        orig = model._lfa_pool
+
+        def timed_lfa(stage, d, coords, nidx, feat, B, N, p, agg):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            orig(stage, d, coords, nidx, feat, B, N, p, agg)
+            b.record()
+            timers.append((stage, d, B * N, a, b))
+        model._lfa_pool = timed_lfa
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = L.lib().o3dml_launch_count()
+    ms = timed_region(step_resident, args.steps, dist_on, dev)
+    launches = L.lib().o3dml_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    if hasattr(model, "_lfa_pool"):
+        model._lfa_pool = orig
+    # --- e2e
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed_region(step_e2e, args.steps, dist_on, dev)
+    pts_step = wl.points_per_step() * world
+    value = pts_step * args.steps / (ms * 1e-3) / 1e6
+    e2e_v = pts_step * args.steps / (ms_e2e * 1e-3) / 1e6
+    outs = step_resident()
+    outs = outs if isinstance(outs, (tuple, list)) else (outs,)
+    # post-batch exchange (outside the timed region): every rank proves it produced a result
+    chk = torch.stack([o.float().abs().mean() for o in outs]).sum().reshape(1)
+    if dist_on:
+        gathered = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+        chk = torch.cat(gathered)
+    assert bool(torch.isfinite(chk).all())
+
+    if rank != 0:
+        if dist_on:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    roof = None
+    if timers:
+        tot_ms = sum(a.elapsed_time(b) for _, _, _, a, b in timers)
+        tot_bytes = sum(wl.roofline_bytes(d, n) for _, d, n, _, _ in timers)
+        tot_flops = sum(wl.roofline_flops(d, s, n) for s, d, n, _, _ in timers)
+        per = {}
+        for s, d, n, a, b in timers:
+            k = "lfa_pool<d=%d,stage=%d>" % (d, s)
+            e = per.setdefault(k, [0.0, 0, 0.0, 0])
+            e[0] += a.elapsed_time(b)
+            e[1] += 1
+            e[2] += wl.roofline_bytes(d, n)
+            e[3] += wl.roofline_flops(d, s, n)
+        ach = tot_bytes / (tot_ms * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel="lfa_pool_kernel (all 8 launches per step)",
+                    achieved=round(ach, 2), peak=pk["hbm_gbs"], unit="GB/s", frac=round(ach / pk["hbm_gbs"], 5),
+                    traffic=None, peak_source=pk["src"],
+                    share_of_step=round(tot_ms / ms, 4),
+                    fp32_tflops=round(tot_flops / (tot_ms * 1e-3) / 1e12, 3),
+                    per_kernel={k: dict(avg_us=round(1e3 * e[0] / e[1], 2),
+                                        gbs=round(e[2] / (e[0] * 1e-3) / 1e9, 1),
+                                        tflops=round(e[3] / (e[0] * 1e-3) / 1e12, 2))
+                                for k, e in sorted(per.items())})
+    # --- cpu baseline (bounded sample, N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        torch.set_num_threads(os.cpu_count())
+        cin = wl.build_inputs_cpu(1)
+        with torch.no_grad():
+            wl.cpu_forward(sd, cin)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                ref = wl.cpu_forward(sd, cin)
+            dt = (time.perf_counter() - t0) / reps
+        cpu = dict(value=round(wl.N / dt / 1e6, 5), unit="Mpoints/s", cores=torch.get_num_threads(),
+                   kind="port", sample="1 unit of %d pts, %d forwards, oracle/models_torch.py" % (wl.N, reps))
+    bi, bo = nbytes(host_inp), sum(nbytes(o) for o in outs)
+    line = dict(metric="M points/s forward", value=round(value, 3), unit="Mpoints/s", n_gpus=world,
+                steps=args.steps, warmup=args.warmup, ms_per_step=round(ms / args.steps, 4),
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=wl.name, units_per_gpu=wl.B, points_per_unit=wl.N,
+                            parallelism="frame-shard x%d, no data-path collective" % world,
+                            l2="inputs + activations per step (%.0f MB inputs) exceed the 126 MB L2; no flush"
+                               % (bi / 1e6)),
+                clocks=clk, e2e=dict(value=round(e2e_v, 3), unit="Mpoints/s", h2d_bytes_per_step=bi,
+                                     d2h_bytes_per_step=bo, ms_per_step=round(ms_e2e / args.steps, 4)),
+                gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
+    print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="randlanet", choices=["randlanet", "pointpillars"])
+    ap.add_argument("--units", type=int, default=0, help="clouds / frames per GPU (0 = config default)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    wl = RandLAWorkload(args.units or 8) if args.workload == "randlanet" else PointPillarsWorkload(args.units or 1)
+    if args.impl == "reference":
+        args.steps = min(args.steps, 50)   # bounded CPU sample: each step is one full-size unit
+        run_reference(args, wl)
+    else:
+        run_b200(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,8 @@ extern "C" {
 
 O3DML_API int o3dml_abi_version(void);
 O3DML_API const char* o3dml_last_error(void);
+/* number of CUDA kernels this library has enqueued in the process (bench.py: gpu_launches) */
+O3DML_API unsigned long long o3dml_launch_count(void);
 
 /* ------------------------------------------------------------------ ops ---- */
 

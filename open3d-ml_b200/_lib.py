@@ -28,6 +28,7 @@ P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
 _SIGNATURES = {
     "o3dml_abi_version": (c_int, []),
     "o3dml_last_error": (ctypes.c_char_p, []),
+    "o3dml_launch_count": (ctypes.c_ulonglong, []),
     "o3dml_voxelize_workspace_bytes": (Z, [L, L]),
     "o3dml_voxelize": (I, [P, L, I, P, L, P, P, P, L, L, P, P, P, P, P, P, P, Z, P]),
     "o3dml_ragged_to_dense": (I, [P, I, L, P, L, L, L, L, P, P]),

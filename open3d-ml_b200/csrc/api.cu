@@ -2,6 +2,7 @@
 #include "../../include/o3dml_b200.h"
 #include "common.cuh"
 #include <stdarg.h>
+#include <atomic>
 
 static thread_local char g_err[512] = "";
 
@@ -13,3 +14,7 @@ extern "C" void o3dml_set_error(const char* fmt, ...) {
 }
 extern "C" const char* o3dml_last_error(void) { return g_err; }
 extern "C" int o3dml_abi_version(void) { return O3DML_ABI_VERSION; }
+
+static std::atomic<unsigned long long> g_launches{0};
+extern "C" void o3dml_count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+extern "C" unsigned long long o3dml_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -11,6 +11,7 @@
 #define O3DML_ERR_UNSUPPORTED 4
 
 extern "C" void o3dml_set_error(const char* fmt, ...);
+extern "C" void o3dml_count_launches(int n);  // kernels enqueued (bench.py gpu_launches)
 
 #define O3DML_FAIL(code, ...)      \
     do {                           \

@@ -305,6 +305,7 @@ static int gemm_launch(const GemmParams& p, cudaStream_t st) {
         gemm_gather_kernel<128><<<grid, GEMM_THREADS, 0, st>>>(p);
     }
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
     return O3DML_OK;
 }
 

@@ -396,6 +396,7 @@ static int grid_build(const float* pts, int64_t np, const int64_t* psplits, cons
         query_order_kernel<<<(unsigned)ceil_div<int64_t>(nq, T), T, 0, st>>>(nq, g.qcell, g.qstart, g.qcursor, g.order);
     }
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(6 + (nq > 0 ? 3 : 0));
     return O3DML_OK;
 }
 
@@ -437,6 +438,7 @@ extern "C" int o3dml_knn_search(const float* points, int64_t num_points,
     else KNN_LAUNCH(64);
 #undef KNN_LAUNCH
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
     return O3DML_OK;
 }
 
@@ -482,6 +484,7 @@ extern "C" int o3dml_radius_count(const float* points, int64_t num_points,
     widen_splits_kernel<<<(unsigned)ceil_div<int64_t>(num_queries, 256), 256, 0, st>>>(
         counts, num_queries, total, neighbors_row_splits, d_total);
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(3);
     return O3DML_OK;
 }
 
@@ -504,5 +507,6 @@ extern "C" int o3dml_radius_fill(const float* queries, int64_t num_points, int64
                                          g.info, g.cell_start, g.sorted, radius, nullptr,
                                          neighbors_row_splits, neighbors_index, neighbors_distance2);
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
     return O3DML_OK;
 }

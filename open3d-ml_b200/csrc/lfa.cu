@@ -159,15 +159,16 @@ lfa_pool_kernel(const __grid_constant__ LfaParams p) {
         float acc[LFA_K][2];
 #pragma unroll
         for (int j = 0; j < LFA_K; ++j) acc[j][0] = acc[j][1] = 0.f;
-        for (int k0 = 0; k0 < H; k0 += LFA_BK) {
-            for (int i = tid; i < LFA_BK * H / 4; i += LFA_THREADS) {
+        constexpr int BK2 = H < LFA_BK ? H : LFA_BK;  // d_out = 16 has only 8 input channels
+        for (int k0 = 0; k0 < H; k0 += BK2) {
+            for (int i = tid; i < BK2 * H / 4; i += LFA_THREADS) {
                 const int kk = i / (H / 4), c = (i % (H / 4)) * 4;
                 *reinterpret_cast<float4*>(&Wsl[kk * H + c]) =
                     *reinterpret_cast<const float4*>(p.wl2t + (size_t)(k0 + kk) * H + c);
             }
             __syncthreads();
 #pragma unroll
-            for (int kk = 0; kk < LFA_BK; ++kk) {
+            for (int kk = 0; kk < BK2; ++kk) {
                 const float* arow = R1t + (size_t)(k0 + kk) * RS + rbase;
                 float a[LFA_K];
 #pragma unroll
@@ -273,6 +274,7 @@ static int lfa_launch(const LfaParams& p, cudaStream_t st) {
     const unsigned blocks = (unsigned)ceil_div<int64_t>(p.total, C::P);
     lfa_pool_kernel<D, STAGE><<<blocks, LFA_THREADS, smem, st>>>(p);
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
     return O3DML_OK;
 }
 

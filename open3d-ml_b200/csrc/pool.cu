@@ -147,6 +147,7 @@ extern "C" int o3dml_gather_max(const float* src, int64_t src_rows, int channels
         src, src_rows, channels, src_ld, index, index_is64, num_rows, k, out_rows_per_batch,
         src_rows_per_batch, shadow_zero, out, out_ld);
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
     return O3DML_OK;
 }
 
@@ -165,5 +166,6 @@ extern "C" int o3dml_kpconv_gather(const float* query_points, int64_t num_querie
         features, in_channels, kernel_points, num_kernel_points, kp_extent, num_queries,
         weighted_features);
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
     return O3DML_OK;
 }

@@ -409,6 +409,7 @@ extern "C" int o3dml_voxelize(const float* points, int64_t num_points, int point
     vox_emit_points_kernel<<<nb, T, 0, st>>>(ks, vs, flags, head_pos, &scalars[0], kept, kept_excl, n,
                                              voxel_point_indices);
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(9 + 3 * ((num_bits + 7) / 8));  // scans here are single-block (n < 64 Ki tiles)
     return O3DML_OK;
 }
 
@@ -430,6 +431,7 @@ extern "C" int o3dml_ragged_to_dense(const void* values, int elem_bytes, int64_t
                                                            out_col_size, inner, (int32_t)fill_bits,
                                                            (int32_t)add, (int32_t*)out);
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
     return O3DML_OK;
 }
 
@@ -456,5 +458,6 @@ extern "C" int o3dml_pp_pfn_scatter(const float* points, int point_stride, int p
         voxel_batch_id, d_num_voxels, num_voxels_bound, w_t, bn_scale, bn_shift, vx, vy, x_offset,
         y_offset, nx, ny, max_points_per_voxel, feat_out, canvas, canvas_nchw);
     O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
     return O3DML_OK;
 }

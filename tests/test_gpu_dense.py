@@ -97,9 +97,9 @@ def test_deconv_nhwc_into_concat_buffer(stride):
     s, t = rnd(Co, seed=3).abs() + 0.5, rnd(Co, seed=4)
     neck = torch.zeros(B, H * stride, W * stride, 384).cuda()
     wt = w.permute(0, 2, 3, 1).reshape(C, stride * stride * Co).contiguous()
-    L.check(L.lib().o3dml_deconv_nhwc(L.ptr(x), B, H, W, C, stride, L.ptr(wt), L.ptr(s.repeat(stride * stride)),
-                                      L.ptr(t.repeat(stride * stride)), 1, 0.0, neck.data_ptr() + 4 * 128, 384, Co,
-                                      L.stream()))
+    s_rep, t_rep = s.repeat(stride * stride), t.repeat(stride * stride)   # keep alive across the call
+    L.check(L.lib().o3dml_deconv_nhwc(L.ptr(x), B, H, W, C, stride, L.ptr(wt), L.ptr(s_rep), L.ptr(t_rep), 1, 0.0,
+                                      neck.data_ptr() + 4 * 128, 384, Co, L.stream()))
     ref = F.conv_transpose2d(x.permute(0, 3, 1, 2), w, None, stride)
     ref = torch.relu(ref * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
     assert rel_err(neck[..., 128:256], ref) < TOL
