@@ -45,6 +45,7 @@ _SIGNATURES = {
     "o3dml_randla_lfa_pool": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
     "o3dml_gather_max": (I, [P, L, I, I, P, I, L, I, L, L, I, P, I, P]),
     "o3dml_kpconv_gather": (I, [P, L, P, L, P, I, I, P, I, P, I, F, P, P]),
+    "o3dml_tc_gemm_test": (I, [P, P, P, I, I, I, P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -1,0 +1,145 @@
+// tc.cuh -- hand-written tcgen05 / TMEM / mbarrier primitives for sm_100a (inline PTX).
+//
+// Operand convention used by every tensor-core kernel in this library:
+//   * 16-bit operands (fp16), K-major, NO swizzle, "chunk-major" canonical layout
+//         element (row r, k)  ->  byte  (k / 8) * (ROWS * 16) + r * 16 + (k % 8) * 2
+//     i.e. [K/8][ROWS][8 halves]: a thread that owns 8 consecutive k of one row writes ONE
+//     16-byte shared store, consecutive rows are consecutive 16-byte words (conflict-free),
+//     and the UMMA descriptor is  LBO = ROWS*16 (next 8-wide k chunk), SBO = 128 (next 8 rows).
+//   * D = A[M x K] * B[N x K]^T accumulates in TMEM (fp32), lane = row of A, column = row of B.
+//   * 22-bit "3xFP16" precision: x = h1 + h2 with h1 = fp16(x), h2 = fp16(x - h1);
+//     A*B ~= A1*B1 + A1*B2 + A2*B1 (three MMAs into the same accumulator).  Relative error
+//     ~2^-21 per product, which keeps the 1e-4 parity bar that plain TF32/BF16 cannot
+//     (SURVEY.md section 7).  Valid for |x| < 65504 (post-BN activations and weights are O(1)).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace o3dml {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core reads)
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// ---- TMEM allocation (one full warp executes these) -----------------------------------------
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
+    static_assert(NCOLS == 32 || NCOLS == 64 || NCOLS == 128 || NCOLS == 256 || NCOLS == 512, "pow2 >= 32");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// ---- descriptors ----------------------------------------------------------------------------
+// shared-memory matrix descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor bit layout:
+// start[0,14) lbo[16,30) sbo[32,46) version[46,48)=1 layout_type[61,64)=0; all in 16-byte units)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fffu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// instruction descriptor for kind::f16, fp16 x fp16 -> fp32, both operands K-major
+// (cute::UMMA::InstrDescriptor: c_format[4,6)=1 a_format[7,10)=0 b_format[10,13)=0
+//  a_major[15]=0 b_major[16]=0 n_dim[17,23)=N>>3 m_dim[24,29)=M>>4)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when they complete
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(bar))
+                 : "memory");
+}
+
+// ---- TMEM -> registers: 32 lanes x 32 bit, 16 consecutive columns per thread ----------------
+// The calling warp reads lanes [32*(warp%4), +32); thread t gets lane 32*(warp%4)+t.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- fp32 -> (h1, h2) split -----------------------------------------------------------------
+__device__ __forceinline__ void split_f16(float x, __half& h1, __half& h2) {
+    x = fminf(fmaxf(x, -65504.f), 65504.f);
+    h1 = __float2half_rn(x);
+    h2 = __float2half_rn(x - __half2float(h1));
+}
+// 8 consecutive-k floats of one row -> two 16-byte words (hi parts, lo parts)
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    __half2 t = __halves2half2(a, b);  // a -> low 16 bits (lower k)
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+    __half h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_f16(x[i], h[i], l[i]);
+    hi = make_uint4(pack_h2(h[0], h[1]), pack_h2(h[2], h[3]), pack_h2(h[4], h[5]), pack_h2(h[6], h[7]));
+    lo = make_uint4(pack_h2(l[0], l[1]), pack_h2(l[2], l[3]), pack_h2(l[4], l[5]), pack_h2(l[6], l[7]));
+}
+
+// byte offset of (row, k-chunk) in the chunk-major canonical layout
+__device__ __forceinline__ uint32_t op_off(int rows, int r, int kchunk) {
+    return (uint32_t)kchunk * (uint32_t)(rows * 16) + (uint32_t)r * 16u;
+}
+
+}  // namespace tc
+}  // namespace o3dml
