@@ -172,6 +172,18 @@ O3DML_API int o3dml_randla_lfa_pool(int stage, int d, const float* coords, const
                           const float* t10, const float* wl2_t, const float* s2, const float* t2,
                           const float* wscore_t, const float* bscore, float* agg, void* stream);
 
+/* Tensor-core (tcgen05, 3xFP16 split) variant of o3dml_randla_lfa_pool, same contract, d in
+ * {16, 32, 64, 128, 256}.  wscore_image / wl2_image: the weight [out][in] packed by the host as
+ * fp16 hi/lo operand images in the UMMA chunk-major layout ([in/8][out][8 halves] hi, then the
+ * same for lo; open3d_ml_b200._lib.pack_operand_image); wl2_t (fp32 [in][out]) is used instead of
+ * wl2_image when d == 16.  The score bias cancels in the softmax and is not taken. */
+O3DML_API int o3dml_randla_lfa_pool_tc(int stage, int d, const float* coords, const void* neighbor_idx,
+                                       int idx_is64, int num_neighbors, const float* feat, int64_t batch,
+                                       int64_t n_per_batch, const float* w10_t, const float* s10,
+                                       const float* t10, const void* wl2_image, const float* wl2_t,
+                                       const float* s2, const float* t2, const void* wscore_image,
+                                       float* agg, void* stream);
+
 /* out[n, :] = max_j src[index[n, j], :]  -- RandLANet.random_sample (randlanet.py:300-327),
  * KPConv max_pool (kpconv.py:840-858, shadow_zero = 1), k = 1: nearest_interpolation /
  * closest_pool. */

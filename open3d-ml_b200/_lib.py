@@ -43,6 +43,7 @@ _SIGNATURES = {
     "o3dml_conv3x3_nhwc": (I, [P, I, I, I, I, I, P, P, P, I, F, P, I, P]),
     "o3dml_deconv_nhwc": (I, [P, I, I, I, I, I, P, P, P, I, F, P, I, I, P]),
     "o3dml_randla_lfa_pool": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
+    "o3dml_randla_lfa_pool_tc": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
     "o3dml_gather_max": (I, [P, L, I, I, P, I, L, I, L, L, I, P, I, P]),
     "o3dml_kpconv_gather": (I, [P, L, P, L, P, I, I, P, I, P, I, F, P, P]),
     "o3dml_tc_gemm_test": (I, [P, P, P, I, I, I, P]),
@@ -124,3 +125,18 @@ def linear(srcs, weight_t, out, scale=None, shift=None, residual=None, act=None,
                              act_code(act), float(slope), ptr(out), ld, co, out_nchw_plane,
                              stream()))
     return out
+
+
+def pack_operand_image(w_nk):
+    """fp32 [N, K] (K contiguous, i.e. nn.Linear's [out, in]) -> uint8 CUDA tensor holding the
+    3xFP16 operand images of csrc/tc.cuh: [K/8][N][8 halves] of hi = fp16(w), then the same
+    layout of lo = fp16(w - hi)."""
+    w = w_nk.detach().to(torch.float32).cpu().clamp(-65504.0, 65504.0)
+    n, k = w.shape
+    assert k % 8 == 0 and n % 8 == 0
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+
+    def img(h):
+        return h.view(n, k // 8, 8).permute(1, 0, 2).contiguous().view(-1)
+    return torch.cat([img(hi), img(lo)]).view(torch.uint8).cuda()

@@ -1,0 +1,442 @@
+// lfa_tc.cu -- RandLA-Net attentive-pooling stage on the 5th-gen tensor cores (tcgen05):
+//   neighbour gather -> LocSE encoding (+ shared MLPs) -> score GEMM on tcgen05 with the
+//   3xFP16 split (tc.cuh) -> softmax over the 16 neighbours -> weighted sum  ==> agg [N, d]
+// Same contract as lfa_pool_kernel (lfa.cu); replaces randlanet.py:521-639 as used at :667-692.
+//
+// One MMA tile = 128 neighbour rows = 8 points x 16 neighbours:
+//   A  [128 x d]  : X = [feat[nbr] | r1 or r2], built by the CTA in shared memory directly in the
+//                   UMMA chunk-major layout (one conflict-free 16-byte store per (row, 8 channels)),
+//                   as fp16 hi/lo pairs.  In stage 2 the first half of A first holds r1 (the A
+//                   operand of the lse2 GEMM) and is then overwritten by the gathered features.
+//   B  [d x d]    : score weight, host-packed hi/lo operand image; resident in shared memory for
+//                   d <= 128, streamed through a 2-slot ring of 32-channel slices for d = 256
+//   D  [128 x d]  : fp32 in TMEM, lane = neighbour row, column = score channel
+// Epilogue: thread = one neighbour row (TMEM lane); softmax over the 16 rows of a point is a
+// half-warp reduction (redux.sync max on order-preserving ints, reduce-scatter shuffles for the
+// two sums), after which lane j of the half-warp owns output channel c0+j -> coalesced stores.
+// Stage 2 chains a second MMA (r2 = lrelu(BN(Wl2 . r1)), N = d/2) through TMEM back into A
+// (d = 16: that 8x8 product stays in registers).  The score bias is not applied: it is constant
+// over the neighbours of a point and cancels in the softmax.  CTAs are persistent over tiles.
+#include "../../include/o3dml_b200.h"
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace o3dml {
+
+constexpr int LTC_THREADS = 256;
+constexpr int LTC_ROWS = 128;  // MMA M
+constexpr int LTC_K = 16;      // neighbours
+constexpr int LTC_SLICE = 32;  // channels per streamed weight slice
+
+struct LfaTcParams {
+    const float* coords;
+    const void* nidx;
+    int nidx_is64;
+    const float* feat;     // [B*N, D/2]
+    int64_t total, n_per_batch;
+    const float* w10t;     // [10][D/2]
+    const float* s10;
+    const float* t10;
+    const uint4* wl2_img;  // stage 2, d >= 32: [hi | lo] operand images of Wl2 [N=D/2][K=D/2]
+    const float* wl2t;     // stage 2, d == 16: fp32 [in][out]
+    const float* s2;
+    const float* t2;
+    const uint4* ws_img;   // [hi | lo] operand images of the score weight [N=D][K=D]
+    float* agg;            // [B*N, D]
+    int64_t num_tiles;
+};
+
+template <int D, int STAGE>
+struct LtcCfg {
+    static constexpr int H = D / 2;
+    static constexpr bool STREAM = D > 128;          // weights do not fit next to the A tile
+    static constexpr bool MMA2 = STAGE == 2 && H >= 16;  // lse2 on the tensor core
+    static constexpr int A_BYTES = D / 8 * LTC_ROWS * 16;  // one of hi / lo
+    static constexpr int B_BYTES = STREAM ? 0 : D / 8 * D * 16;
+    static constexpr int B2_BYTES = (MMA2 && !STREAM) ? H / 8 * H * 16 : 0;
+    static constexpr int RING_SLOT = STREAM ? 2 * (LTC_SLICE / 8) * D * 16 : 0;  // hi + lo of one slice
+    static constexpr int W10_BYTES = 12 * H * 4;
+    static constexpr int ST2_BYTES = STAGE == 2 ? (2 * H + (H < 16 ? H * H : 0)) * 4 : 0;
+    static constexpr int TMEM_NEED = D + (MMA2 ? H : 0);
+    static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128
+                                     : TMEM_NEED <= 256 ? 256 : 512;
+    static constexpr size_t SMEM = 2 * A_BYTES + 2 * B_BYTES + 2 * B2_BYTES + 2 * RING_SLOT + W10_BYTES +
+                                   ST2_BYTES + 128;
+};
+
+// D[tmem_d] = A[128 x K] * B[N x K]^T, all operands resident in shared memory; one thread.
+template <int N, int K>
+__device__ __forceinline__ void issue_resident(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo,
+                                               const uint8_t* b_hi, const uint8_t* b_lo) {
+    constexpr uint32_t idesc = tc::idesc_f16(LTC_ROWS, N);
+    constexpr uint32_t A_LBO = LTC_ROWS * 16, B_LBO = N * 16;
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t ah = tc::smem_desc(tc::smem_u32(a_hi) + ks * 2 * A_LBO, A_LBO, 128);
+        const uint64_t al = tc::smem_desc(tc::smem_u32(a_lo) + ks * 2 * A_LBO, A_LBO, 128);
+        const uint64_t bh = tc::smem_desc(tc::smem_u32(b_hi) + ks * 2 * B_LBO, B_LBO, 128);
+        const uint64_t bl = tc::smem_desc(tc::smem_u32(b_lo) + ks * 2 * B_LBO, B_LBO, 128);
+        tc::umma_f16(tmem_d, ah, bh, idesc, ks > 0);
+        tc::umma_f16(tmem_d, ah, bl, idesc, 1);
+        tc::umma_f16(tmem_d, al, bh, idesc, 1);
+    }
+}
+
+// Same product with B streamed from global memory (host-packed images) through a 2-slot ring
+// of 32-channel slices; the copy of slice s+1 overlaps the MMAs of slice s.  Called by ALL
+// threads; returns when the accumulator is complete.  ph[] = wait parities of the ring barriers.
+template <int N, int K>
+__device__ __forceinline__ void gemm_streamed(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo,
+                                              const uint4* __restrict__ img, uint8_t* ring, int slot_bytes,
+                                              uint64_t* mb_ring, uint32_t* ph, int tid) {
+    constexpr uint32_t idesc = tc::idesc_f16(LTC_ROWS, N);
+    constexpr uint32_t A_LBO = LTC_ROWS * 16, B_LBO = N * 16;
+    constexpr int CH = LTC_SLICE / 8;                 // 16-byte k-chunks per slice
+    constexpr int SL_U4 = CH * N;                     // uint4 per slice per image
+    constexpr int IMG_U4 = K / 8 * N;                 // uint4 per image (hi, then lo)
+    constexpr int NSL = K / LTC_SLICE;
+    auto copy_slice = [&](int s, int slot) {
+        uint4* dst = reinterpret_cast<uint4*>(ring + (size_t)slot * slot_bytes);
+        const uint4* src_hi = img + (size_t)s * SL_U4;
+        const uint4* src_lo = img + IMG_U4 + (size_t)s * SL_U4;
+        for (int i = tid; i < SL_U4; i += LTC_THREADS) {
+            dst[i] = src_hi[i];
+            dst[SL_U4 + i] = src_lo[i];
+        }
+        tc::fence_async_smem();
+    };
+    copy_slice(0, 0);
+    __syncthreads();
+    for (int s = 0; s < NSL; ++s) {
+        const int slot = s & 1;
+        if (tid == 0) {
+            const uint8_t* b_hi = ring + (size_t)slot * slot_bytes;
+            const uint8_t* b_lo = b_hi + (size_t)SL_U4 * 16;
+#pragma unroll
+            for (int ks = 0; ks < LTC_SLICE / 16; ++ks) {
+                const int kc = s * CH + ks * 2;  // first k-chunk of this k-step in A
+                const uint64_t ah = tc::smem_desc(tc::smem_u32(a_hi) + kc * A_LBO, A_LBO, 128);
+                const uint64_t al = tc::smem_desc(tc::smem_u32(a_lo) + kc * A_LBO, A_LBO, 128);
+                const uint64_t bh = tc::smem_desc(tc::smem_u32(b_hi) + ks * 2 * B_LBO, B_LBO, 128);
+                const uint64_t bl = tc::smem_desc(tc::smem_u32(b_lo) + ks * 2 * B_LBO, B_LBO, 128);
+                tc::umma_f16(tmem_d, ah, bh, idesc, (s | ks) > 0);
+                tc::umma_f16(tmem_d, ah, bl, idesc, 1);
+                tc::umma_f16(tmem_d, al, bh, idesc, 1);
+            }
+            tc::umma_commit(&mb_ring[slot]);
+        }
+        if (s + 1 < NSL) {
+            if (s >= 1) {  // slot (s+1)&1 was read by slice s-1: wait until those MMAs are done
+                tc::mbar_wait(&mb_ring[(s + 1) & 1], ph[(s + 1) & 1]);
+                ph[(s + 1) & 1] ^= 1;
+            }
+            copy_slice(s + 1, (s + 1) & 1);
+        }
+        __syncthreads();
+    }
+    // the commits of the last two slices have not been waited for yet
+    if (NSL >= 2) {
+        tc::mbar_wait(&mb_ring[(NSL - 2) & 1], ph[(NSL - 2) & 1]);
+        ph[(NSL - 2) & 1] ^= 1;
+    }
+    tc::mbar_wait(&mb_ring[(NSL - 1) & 1], ph[(NSL - 1) & 1]);
+    ph[(NSL - 1) & 1] ^= 1;
+    tc::tc_fence_after();
+}
+
+template <int D, int STAGE>
+__global__ void __launch_bounds__(LTC_THREADS, 1)
+lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
+    using C = LtcCfg<D, STAGE>;
+    constexpr int H = C::H;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* a_hi = smem;
+    uint8_t* a_lo = a_hi + C::A_BYTES;
+    uint8_t* b_hi = a_lo + C::A_BYTES;
+    uint8_t* b_lo = b_hi + C::B_BYTES;
+    uint8_t* b2_hi = b_lo + C::B_BYTES;
+    uint8_t* b2_lo = b2_hi + C::B2_BYTES;
+    uint8_t* ring = b2_lo + C::B2_BYTES;
+    float* W10 = reinterpret_cast<float*>(ring + 2 * C::RING_SLOT);  // [12][H]
+    float* ST2 = W10 + 12 * H;                                       // [2][H] (+ Wl2^T [H][H] for H < 16)
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ST2) + C::ST2_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = tid & (LTC_ROWS - 1);   // neighbour row of the tile this thread works on
+    const int half = tid >> 7;              // which half of the channels / columns
+
+    // ---- once per CTA: weights, barriers, TMEM
+    if (!C::STREAM) {
+        for (int i = tid; i < 2 * C::B_BYTES / 16; i += LTC_THREADS)
+            reinterpret_cast<uint4*>(b_hi)[i] = p.ws_img[i];
+        if (C::MMA2)
+            for (int i = tid; i < 2 * C::B2_BYTES / 16; i += LTC_THREADS)
+                reinterpret_cast<uint4*>(b2_hi)[i] = p.wl2_img[i];
+    }
+    if (STAGE == 2) {
+        for (int i = tid; i < H; i += LTC_THREADS) {
+            ST2[i] = p.s2[i];
+            ST2[H + i] = p.t2[i];
+        }
+        if (H < 16)
+            for (int i = tid; i < H * H; i += LTC_THREADS) ST2[2 * H + i] = p.wl2t[i];
+    }
+    for (int i = tid; i < 10 * H; i += LTC_THREADS) W10[i] = p.w10t[i];
+    for (int i = tid; i < H; i += LTC_THREADS) {
+        W10[10 * H + i] = p.s10[i];
+        W10[11 * H + i] = p.t10[i];
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&mbar[i], 1);
+        tc::fence_mbar_init();
+    }
+    tc::fence_async_smem();
+    __syncthreads();
+    if (warp == 0) tc::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t ph_main[2] = {0, 0};  // parities of mbar[0] (lse2) and mbar[1] (scores)
+    uint32_t ph_ring[2] = {0, 0};  // parities of mbar[2], mbar[3] (weight ring)
+
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        // ---------------- neighbour id + 10-channel encoding of this thread's row
+        const int64_t g = tile * (LTC_ROWS / LTC_K) + (row >> 4);
+        int64_t nb = -1;
+        float e[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) e[q] = 0.f;
+        if (g < p.total) {
+            const int64_t b = g / p.n_per_batch;
+            nb = b * p.n_per_batch + load_index(p.nidx, g * LTC_K + (row & 15), p.nidx_is64);
+            const float qx = p.coords[3 * g], qy = p.coords[3 * g + 1], qz = p.coords[3 * g + 2];
+            const float cx = p.coords[3 * nb], cy = p.coords[3 * nb + 1], cz = p.coords[3 * nb + 2];
+            const float dx = qx - cx, dy = qy - cy, dz = qz - cz;
+            e[0] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+            e[1] = dx; e[2] = dy; e[3] = dz;
+            e[4] = qx; e[5] = qy; e[6] = qz;
+            e[7] = cx; e[8] = cy; e[9] = cz;
+        }
+        // ---------------- r1 = lrelu(BN(W10 . enc)), 8 outputs at a time, straight into the operand:
+        //   stage 1            -> channels [H, D) of A
+        //   stage 2, tensor    -> channels [0, H) of A (A operand of the lse2 GEMM)
+        //   stage 2, H < 16    -> r2 = lrelu(BN(Wl2 . r1)) in registers -> channels [H, D)
+        for (int ch = half; ch < H / 8; ch += 2) {
+            float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int o = ch * 8 + j;
+                float a = 0.f;
+#pragma unroll
+                for (int q = 0; q < 10; ++q) a = fmaf(e[q], W10[q * H + o], a);
+                a = fmaf(a, W10[10 * H + o], W10[11 * H + o]);
+                r[j] = a >= 0.f ? a : 0.2f * a;
+            }
+            int dst_chunk = H / 8 + ch;
+            if (STAGE == 2) {
+                if (C::MMA2) {
+                    dst_chunk = ch;
+                } else {  // H == 8: one chunk holds all of r1
+                    float r2[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float a = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a = fmaf(r[i], ST2[2 * H + i * H + j], a);
+                        a = fmaf(a, ST2[j], ST2[H + j]);
+                        r2[j] = a >= 0.f ? a : 0.2f * a;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = r2[j];
+                }
+            }
+            uint4 hi, lo;
+            tc::split8(r, hi, lo);
+            *reinterpret_cast<uint4*>(a_hi + tc::op_off(LTC_ROWS, row, dst_chunk)) = hi;
+            *reinterpret_cast<uint4*>(a_lo + tc::op_off(LTC_ROWS, row, dst_chunk)) = lo;
+        }
+
+        // ---------------- stage 2: r2 = lrelu(BN(Wl2 . r1)) on the tensor core -> channels [H, D)
+        if (C::MMA2) {
+            tc::fence_async_smem();
+            tc::tc_fence_before();
+            __syncthreads();
+            tc::tc_fence_after();
+            if (C::STREAM) {
+                gemm_streamed<H, H>(tmem + D, a_hi, a_lo, p.wl2_img, ring, C::RING_SLOT, &mbar[2], ph_ring, tid);
+            } else {
+                if (tid == 0) {
+                    issue_resident<H, H>(tmem + D, a_hi, a_lo, b2_hi, b2_lo);
+                    tc::umma_commit(&mbar[0]);
+                }
+                tc::mbar_wait(&mbar[0], ph_main[0]);
+                ph_main[0] ^= 1;
+                tc::tc_fence_after();
+            }
+            for (int c0 = half * 8; c0 < H; c0 += 16) {
+                float v[8];
+                tc::tmem_ld8(tmem_lane + D + c0, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float a = fmaf(v[j], ST2[c0 + j], ST2[H + c0 + j]);
+                    v[j] = a >= 0.f ? a : 0.2f * a;
+                }
+                uint4 hi, lo;
+                tc::split8(v, hi, lo);
+                *reinterpret_cast<uint4*>(a_hi + tc::op_off(LTC_ROWS, row, (H + c0) / 8)) = hi;
+                *reinterpret_cast<uint4*>(a_lo + tc::op_off(LTC_ROWS, row, (H + c0) / 8)) = lo;
+            }
+        }
+        // ---------------- gathered neighbour features -> channels [0, H)  (overwrites r1 in stage 2:
+        // the lse2 MMAs that read it have completed)
+        for (int ch = half; ch < H / 8; ch += 2) {
+            float x[8];
+            if (nb >= 0) {
+                const float4 v0 = *reinterpret_cast<const float4*>(p.feat + (size_t)nb * H + ch * 8);
+                const float4 v1 = *reinterpret_cast<const float4*>(p.feat + (size_t)nb * H + ch * 8 + 4);
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = 0.f;
+            }
+            uint4 hi, lo;
+            tc::split8(x, hi, lo);
+            *reinterpret_cast<uint4*>(a_hi + tc::op_off(LTC_ROWS, row, ch)) = hi;
+            *reinterpret_cast<uint4*>(a_lo + tc::op_off(LTC_ROWS, row, ch)) = lo;
+        }
+        tc::fence_async_smem();
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+
+        // ---------------- scores = X . Ws^T on the tensor core
+        if (C::STREAM) {
+            gemm_streamed<D, D>(tmem, a_hi, a_lo, p.ws_img, ring, C::RING_SLOT, &mbar[2], ph_ring, tid);
+        } else {
+            if (tid == 0) {
+                issue_resident<D, D>(tmem, a_hi, a_lo, b_hi, b_lo);
+                tc::umma_commit(&mbar[1]);
+            }
+            tc::mbar_wait(&mbar[1], ph_main[1]);
+            ph_main[1] ^= 1;
+            tc::tc_fence_after();
+        }
+
+        // ---------------- softmax over the 16 rows of each point + weighted sum
+        const unsigned gmask = 0xffffu << (lane & 16);
+        const int j16 = lane & 15;
+        for (int c0 = half * 16; c0 < D; c0 += 32) {
+            float s[16], x[16];
+            tc::tmem_ld16(tmem_lane + c0, s);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint4 hq = *reinterpret_cast<const uint4*>(a_hi + tc::op_off(LTC_ROWS, row, c0 / 8 + q));
+                const uint4 lq = *reinterpret_cast<const uint4*>(a_lo + tc::op_off(LTC_ROWS, row, c0 / 8 + q));
+                const __half2* hh = reinterpret_cast<const __half2*>(&hq);
+                const __half2* ll = reinterpret_cast<const __half2*>(&lq);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float2 fh = __half22float2(hh[u]), fl = __half22float2(ll[u]);
+                    x[q * 8 + 2 * u] = fh.x + fl.x;
+                    x[q * 8 + 2 * u + 1] = fh.y + fl.y;
+                }
+            }
+            float den[16], num[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                int o = __float_as_int(s[i]);
+                o ^= (o >> 31) & 0x7fffffff;              // order-preserving float -> int
+                int m = __reduce_max_sync(gmask, o);
+                m ^= (m >> 31) & 0x7fffffff;
+                const float ev = __expf(s[i] - __int_as_float(m));
+                den[i] = ev;
+                num[i] = ev * x[i];
+            }
+            // reduce-scatter over the 16 lanes of the group: afterwards lane j16 holds column c0+j16
+#pragma unroll
+            for (int w = 8; w >= 1; w >>= 1) {
+                const bool up = (lane & w) != 0;
+#pragma unroll
+                for (int i = 0; i < w; ++i) {
+                    const float sd = up ? den[i] : den[i + w];
+                    const float sn = up ? num[i] : num[i + w];
+                    const float rd = __shfl_xor_sync(0xffffffffu, sd, w);
+                    const float rn = __shfl_xor_sync(0xffffffffu, sn, w);
+                    den[i] = (up ? den[i + w] : den[i]) + rd;
+                    num[i] = (up ? num[i + w] : num[i]) + rn;
+                }
+            }
+            if (g < p.total) p.agg[(size_t)g * D + c0 + j16] = num[0] / den[0];
+        }
+        tc::tc_fence_before();
+        __syncthreads();   // TMEM accumulators and the A tile are free for the next tile
+        tc::tc_fence_after();
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<C::TMEM_COLS>(tmem);
+}
+
+template <int D, int STAGE>
+static int lfa_tc_launch(const LfaTcParams& p, cudaStream_t st) {
+    using C = LtcCfg<D, STAGE>;
+    static_assert(C::SMEM <= 227 * 1024, "shared memory budget");
+    static bool configured = false;
+    if (!configured) {
+        O3DML_CUDA(cudaFuncSetAttribute(lfa_pool_tc_kernel<D, STAGE>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured = true;
+    }
+    int per_sm = (int)(224 * 1024 / (C::SMEM + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * C::TMEM_COLS > 512) per_sm = 512 / C::TMEM_COLS;
+    if (per_sm > 4) per_sm = 4;
+    int64_t grid = (int64_t)kNumSMs * per_sm;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    lfa_pool_tc_kernel<D, STAGE><<<(unsigned)grid, LTC_THREADS, C::SMEM, st>>>(p);
+    O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
+    return O3DML_OK;
+}
+
+}  // namespace o3dml
+
+using namespace o3dml;
+
+extern "C" int o3dml_randla_lfa_pool_tc(int stage, int d, const float* coords, const void* neighbor_idx,
+                                        int idx_is64, int num_neighbors, const float* feat, int64_t batch,
+                                        int64_t n_per_batch, const float* w10_t, const float* s10,
+                                        const float* t10, const void* wl2_image, const float* wl2_t,
+                                        const float* s2, const float* t2, const void* wscore_image,
+                                        float* agg, void* stream) {
+    O3DML_CHECK(stage == 1 || stage == 2, "lfa_tc: stage must be 1 or 2");
+    O3DML_CHECK(num_neighbors == LTC_K, "lfa_tc: built for 16 neighbours");
+    O3DML_CHECK(batch * n_per_batch < ((int64_t)1 << 31), "lfa_tc: too many points");
+    O3DML_CHECK(stage == 1 || (s2 && t2 && (d == 16 ? wl2_t != nullptr : wl2_image != nullptr)),
+                "lfa_tc: stage 2 needs the lse2 weights");
+    LfaTcParams p;
+    p.coords = coords; p.nidx = neighbor_idx; p.nidx_is64 = idx_is64; p.feat = feat;
+    p.total = batch * n_per_batch; p.n_per_batch = n_per_batch;
+    p.w10t = w10_t; p.s10 = s10; p.t10 = t10;
+    p.wl2_img = (const uint4*)wl2_image; p.wl2t = wl2_t; p.s2 = s2; p.t2 = t2;
+    p.ws_img = (const uint4*)wscore_image; p.agg = agg;
+    p.num_tiles = ceil_div<int64_t>(p.total, LTC_ROWS / LTC_K);
+    if (p.total == 0) return O3DML_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define LTC_CASE(DD) \
+    case DD: return stage == 1 ? lfa_tc_launch<DD, 1>(p, st) : lfa_tc_launch<DD, 2>(p, st);
+    switch (d) {
+        LTC_CASE(16)
+        LTC_CASE(32)
+        LTC_CASE(64)
+        LTC_CASE(128)
+        LTC_CASE(256)
+        default:
+            O3DML_FAIL(O3DML_ERR_UNSUPPORTED, "lfa_tc: d_out %d not in {16,32,64,128,256}", d);
+    }
+#undef LTC_CASE
+}

@@ -20,6 +20,7 @@ import torch
 from . import _lib as L
 
 BN_EPS = 1e-6  # randlanet.py:77,499
+TC_DIMS = (16, 32, 64, 128, 256)  # d_out values served by the tcgen05 kernel (lfa_tc.cu)
 
 
 def _fold_bn(sd, prefix, bias=None, eps=BN_EPS):
@@ -31,8 +32,10 @@ def _fold_bn(sd, prefix, bias=None, eps=BN_EPS):
 
 
 class RandLANetB200:
-    def __init__(self, state_dict, num_layers=4, num_neighbors=16, device=None):
+    def __init__(self, state_dict, num_layers=4, num_neighbors=16, device=None, use_tc=None):
         L.require_cuda()
+        import os
+        self.use_tc = (os.environ.get("O3DML_LFA_TC", "1") != "0") if use_tc is None else bool(use_tc)
         self.device = torch.device(device or "cuda")
         self.num_layers = num_layers
         self.k = num_neighbors
@@ -70,6 +73,12 @@ class RandLANetB200:
                 put("%s.%s.score.b" % (p, pool), sd["%s.%s.score_fn.0.bias" % (p, pool)])
             d = sd[p + ".pool2.mlp.conv.weight"].shape[0]
             self.d_out.append(d)
+            if d in TC_DIMS:   # tcgen05 path: host-packed fp16 hi/lo operand images ([out][in])
+                for pool in ("pool1", "pool2"):
+                    self.w["%s.%s.score.img" % (p, pool)] = L.pack_operand_image(
+                        sd["%s.%s.score_fn.0.weight" % (p, pool)])
+                if d >= 32:
+                    self.w[p + ".lse2.mlp.img"] = L.pack_operand_image(sd[p + ".lse2.mlp.conv.weight"][:, :, 0, 0])
             # mlp2 + shortcut as ONE gemm over [p2 | feat] with the BN scales folded into the rows
             s2, t2 = _fold_bn(sd, p + ".mlp2.batch_norm", sd[p + ".mlp2.conv.bias"])
             ss, ts = _fold_bn(sd, p + ".shortcut.batch_norm", sd[p + ".shortcut.conv.bias"])
@@ -103,6 +112,17 @@ class RandLANetB200:
     def _lfa_pool(self, stage, d, coords, nidx, feat, B, N, p, agg):
         w = self.w
         pool = "pool1" if stage == 1 else "pool2"
+        if self.use_tc and d in TC_DIMS:
+            L.check(L.lib().o3dml_randla_lfa_pool_tc(
+                stage, d, L.ptr(coords), L.ptr(nidx), 1 if nidx.dtype == torch.int64 else 0, self.k,
+                L.ptr(feat), B, N, L.ptr(w[p + ".lse1.mlp.wt"]), L.ptr(w[p + ".lse1.mlp.s"]),
+                L.ptr(w[p + ".lse1.mlp.t"]),
+                L.ptr(w.get(p + ".lse2.mlp.img")) if stage == 2 else None,
+                L.ptr(w[p + ".lse2.mlp.wt"]) if stage == 2 else None,
+                L.ptr(w[p + ".lse2.mlp.s"]) if stage == 2 else None,
+                L.ptr(w[p + ".lse2.mlp.t"]) if stage == 2 else None,
+                L.ptr(w["%s.%s.score.img" % (p, pool)]), L.ptr(agg), L.stream()))
+            return
         L.check(L.lib().o3dml_randla_lfa_pool(
             stage, d, L.ptr(coords), L.ptr(nidx), 1 if nidx.dtype == torch.int64 else 0, self.k,
             L.ptr(feat), B, N, L.ptr(w[p + ".lse1.mlp.wt"]), L.ptr(w[p + ".lse1.mlp.s"]),
