@@ -20,6 +20,7 @@
 #include "../../include/o3dml_b200.h"
 #include "common.cuh"
 #include "tc.cuh"
+#include <limits.h>
 
 namespace o3dml {
 
@@ -106,7 +107,9 @@ __device__ __forceinline__ void gemm_streamed(uint32_t tmem_d, const uint8_t* a_
         tc::fence_async_smem();
     };
     copy_slice(0, 0);
+    tc::tc_fence_before();
     __syncthreads();
+    tc::tc_fence_after();   // order the MMAs issued below after the barrier (operands now visible)
     for (int s = 0; s < NSL; ++s) {
         const int slot = s & 1;
         if (tid == 0) {
@@ -132,7 +135,9 @@ __device__ __forceinline__ void gemm_streamed(uint32_t tmem_d, const uint8_t* a_
             }
             copy_slice(s + 1, (s + 1) & 1);
         }
+        tc::tc_fence_before();
         __syncthreads();
+        tc::tc_fence_after();
     }
     // the commits of the last two slices have not been waited for yet
     if (NSL >= 2) {
@@ -328,7 +333,7 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
         }
 
         // ---------------- softmax over the 16 rows of each point + weighted sum
-        const unsigned gmask = 0xffffu << (lane & 16);
+        const bool upper = (lane & 16) != 0;
         const int j16 = lane & 15;
         for (int c0 = half * 16; c0 < D; c0 += 32) {
             float s[16], x[16];
@@ -351,11 +356,20 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
             for (int i = 0; i < 16; ++i) {
                 int o = __float_as_int(s[i]);
                 o ^= (o >> 31) & 0x7fffffff;              // order-preserving float -> int
-                int m = __reduce_max_sync(gmask, o);
+                // per-half-warp max through two FULL-warp reductions (redux.sync with two different
+                // sub-warp masks in one instruction returned the wrong group's maximum on B200)
+                const int m_lo = __reduce_max_sync(0xffffffffu, upper ? INT_MIN : o);
+                const int m_hi = __reduce_max_sync(0xffffffffu, upper ? o : INT_MIN);
+                int m = upper ? m_hi : m_lo;
                 m ^= (m >> 31) & 0x7fffffff;
                 const float ev = __expf(s[i] - __int_as_float(m));
                 den[i] = ev;
                 num[i] = ev * x[i];
+#ifdef O3DML_DEBUG_NAN
+                if (!(ev <= 1.0f) || !(fabsf(x[i]) < 1e30f) || !(fabsf(s[i]) < 1e30f))
+                    printf("DBG tile %lld row %d c0 %d i %d s %g m %g ev %g x %g o %d mi %d\n",
+                           (long long)tile, row, c0, i, s[i], __int_as_float(m), ev, x[i], o, m);
+#endif
             }
             // reduce-scatter over the 16 lanes of the group: afterwards lane j16 holds column c0+j16
 #pragma unroll

@@ -11,7 +11,7 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def make(d, B, N, seed):
+def make(d, B, N, seed, gain=1.0):
     g = torch.Generator().manual_seed(seed)
     h = d // 2
     coords = (torch.rand(B * N, 3, generator=g) * 10).cuda()
@@ -21,16 +21,18 @@ def make(d, B, N, seed):
     s10, t10 = (torch.rand(h, generator=g) + 0.5).cuda(), (torch.randn(h, generator=g) * 0.1).cuda()
     wl2 = (torch.randn(h, h, generator=g) / h ** 0.5)          # [out, in]
     s2, t2 = (torch.rand(h, generator=g) + 0.5).cuda(), (torch.randn(h, generator=g) * 0.1).cuda()
-    ws = (torch.randn(d, d, generator=g) / d ** 0.5)           # [out, in]
+    ws = (torch.randn(d, d, generator=g) / d ** 0.5) * gain    # [out, in]; gain spreads the scores
     bs = torch.randn(d, generator=g).cuda()
     return coords, nidx, feat, w10, s10, t10, wl2, s2, t2, ws, bs
 
 
 @pytest.mark.parametrize("d", [16, 32, 64, 128, 256])
 @pytest.mark.parametrize("stage", [1, 2])
-@pytest.mark.parametrize("B,N", [(1, 8), (2, 1000), (3, 2817)])
-def test_lfa_tc_matches_simt(d, stage, B, N):
-    coords, nidx, feat, w10, s10, t10, wl2, s2, t2, ws, bs = make(d, B, N, 7 * d + stage)
+@pytest.mark.parametrize("B,N,gain", [(1, 8, 1.0), (2, 1000, 1.0), (3, 2817, 1.0), (2, 500, 40.0)])
+def test_lfa_tc_matches_simt(d, stage, B, N, gain):
+    """gain = 40 makes the scores of neighbouring points differ by hundreds: the softmax max must be
+    taken per point (a wrong group maximum only shows up once exp() underflows)."""
+    coords, nidx, feat, w10, s10, t10, wl2, s2, t2, ws, bs = make(d, B, N, 7 * d + stage, gain)
     ref = torch.full((B * N, d), float("nan")).cuda()
     out = torch.full((B * N, d), float("nan")).cuda()
     wl2t, wst = wl2.t().contiguous().cuda(), ws.t().contiguous().cuda()
@@ -44,4 +46,4 @@ def test_lfa_tc_matches_simt(d, stage, B, N):
                                              L.ptr(s2), L.ptr(t2), L.ptr(img_s), L.ptr(out), L.stream()))
     torch.cuda.synchronize()
     assert not torch.isnan(out).any()
-    assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
+    assert rel_err(out, ref) < (2e-5 if gain == 1.0 else 2e-3), rel_err(out, ref)
