@@ -20,7 +20,9 @@ import torch
 from . import _lib as L
 
 BN_EPS = 1e-6  # randlanet.py:77,499
-TC_DIMS = (16, 32, 64, 128, 256)  # d_out values served by the tcgen05 kernel (lfa_tc.cu)
+# d_out values served by the tcgen05 kernel (lfa_tc.cu).  d = 16 stays on the FP32 SIMT kernel: its
+# 16x16 score product is too small to pay for the per-tile MMA round trip (0.84 vs 1.23 ms measured).
+TC_DIMS = (32, 64, 128, 256)
 
 
 def _fold_bn(sd, prefix, bias=None, eps=BN_EPS):
