@@ -42,6 +42,9 @@ _SIGNATURES = {
     "o3dml_linear": (I, [L, ctypes.POINTER(Src), I, P, P, P, P, I, I, F, P, I, I, I, P]),
     "o3dml_conv3x3_nhwc": (I, [P, I, I, I, I, I, P, P, P, I, F, P, I, P]),
     "o3dml_deconv_nhwc": (I, [P, I, I, I, I, I, P, P, P, I, F, P, I, I, P]),
+    "o3dml_linear_tc": (I, [L, ctypes.POINTER(Src), I, P, I, I, P, P, P, I, I, F, P, I, I, I, P]),
+    "o3dml_conv3x3_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, P, P, I, F, P, I, P]),
+    "o3dml_deconv_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, P, P, I, F, P, I, I, P]),
     "o3dml_randla_lfa_pool": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
     "o3dml_randla_lfa_pool_tc": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
     "o3dml_gather_max": (I, [P, L, I, I, P, I, L, I, L, L, I, P, I, P]),
@@ -113,17 +116,56 @@ def make_src(data, index=None, index_ld=1, out_rows_per_batch=0, src_rows_per_ba
     return s
 
 
-def linear(srcs, weight_t, out, scale=None, shift=None, residual=None, act=None, slope=0.0,
+USE_TC_GEMM = os.environ.get("O3DML_GEMM_TC", "1") != "0"
+
+
+class PackedWeight:
+    """A dense-layer weight in both forms: fp32 [K, Cout] for the SIMT kernel (gemm.cu) and the
+    zero-padded fp16 hi/lo operand image for the tcgen05 kernel (gemm_tc.cu)."""
+
+    def __init__(self, w_kc):
+        w = w_kc.detach().to(torch.float32).cpu().contiguous()
+        self.k, self.cout = w.shape
+        self.wt = w.cuda()
+        self.k_pad = (self.k + 31) // 32 * 32
+        self.n_pad = 32 if self.cout <= 32 else 64 if self.cout <= 64 else (self.cout + 127) // 128 * 128
+        wp = torch.zeros((self.n_pad, self.k_pad), dtype=torch.float32)
+        wp[:self.cout, :self.k] = w.t()
+        self.img = pack_operand_image(wp)
+
+    @property
+    def shape(self):
+        return (self.k, self.cout)
+
+
+def pack_linear(w_kc):
+    return PackedWeight(w_kc)
+
+
+def _tc_ok(srcs):
+    return USE_TC_GEMM and all((s.channels % 8 == 0) and (s.ld % 4 == 0) and (s.data % 16 == 0) for s in srcs)
+
+
+def linear(srcs, weight, out, scale=None, shift=None, residual=None, act=None, slope=0.0,
            num_rows=None, out_channels=None, out_ld=None, out_nchw_plane=0):
-    """out[n,:] = act(scale * (concat(srcs)[n] @ weight_t) + shift + residual[n])."""
+    """out[n,:] = act(scale * (concat(srcs)[n] @ W) + shift + residual[n]).  `weight` is either an
+    fp32 [K, Cout] tensor (SIMT kernel) or a PackedWeight (tensor-core kernel when the sources
+    allow it)."""
     arr = (Src * len(srcs))(*srcs)
     n = out.shape[0] if num_rows is None else num_rows
-    co = weight_t.shape[1] if out_channels is None else out_channels
+    packed = isinstance(weight, PackedWeight)
+    wt = weight.wt if packed else weight
+    co = wt.shape[1] if out_channels is None else out_channels
     ld = (out.stride(0) if out_nchw_plane == 0 else co) if out_ld is None else out_ld
-    check(lib().o3dml_linear(n, arr, len(srcs), ptr(weight_t), ptr(scale), ptr(shift),
-                             ptr(residual), residual.stride(0) if residual is not None else 0,
-                             act_code(act), float(slope), ptr(out), ld, co, out_nchw_plane,
-                             stream()))
+    res_ld = residual.stride(0) if residual is not None else 0
+    if packed and _tc_ok(srcs):
+        check(lib().o3dml_linear_tc(n, arr, len(srcs), ptr(weight.img), weight.k_pad, weight.n_pad,
+                                    ptr(scale), ptr(shift), ptr(residual), res_ld, act_code(act),
+                                    float(slope), ptr(out), ld, co, out_nchw_plane, stream()))
+    else:
+        check(lib().o3dml_linear(n, arr, len(srcs), ptr(wt), ptr(scale), ptr(shift), ptr(residual),
+                                 res_ld, act_code(act), float(slope), ptr(out), ld, co, out_nchw_plane,
+                                 stream()))
     return out
 
 

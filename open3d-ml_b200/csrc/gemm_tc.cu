@@ -1,0 +1,420 @@
+// gemm_tc.cu -- the gathered GEMM / implicit-GEMM convolution of gemm.cu on the tcgen05 tensor
+// cores.  Same operand model (A rows gathered on the fly: identity / index gather with shadow rows /
+// batch-relative index / 3x3 conv taps; epilogue = folded BN + residual + activation, row-major /
+// NCHW / pixel-shuffle output), but
+//   * A k-slices (32 channels) are converted by the CTA to fp16 hi/lo pairs and written straight into
+//     the UMMA chunk-major shared-memory layout (tc.cuh), 3 MMAs per k-step (3xFP16, ~2^-21 relative),
+//   * B comes from a host-packed hi/lo operand image ([K/8][Cout_pad][8 halves], zero padded),
+//   * the accumulator [128 x BN] lives in TMEM; a 3-stage ring lets the conversion of slice s+1
+//     overlap the MMAs of slice s (global loads of slice s+1 are in flight across the barrier).
+// Serves SharedMLP / UnaryBlock / KPConv [15*Cin, Cout] / SECOND + FPN + head convolutions whenever
+// every source has a multiple of 8 channels; the FP32 SIMT kernel (gemm.cu) takes the rest.
+#include "../../include/o3dml_b200.h"
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace o3dml {
+
+constexpr int GT_THREADS = 256;
+constexpr int GT_ROWS = 128;
+constexpr int GT_KS = 32;       // channels per k-slice
+constexpr int GT_CH = GT_KS / 8;
+constexpr int GT_STAGES = 3;
+constexpr int GT_MAX_SRC = 3;
+
+struct GtSrc {
+    const float* data;
+    const void* index;
+    int64_t rows, out_rows_per_batch, src_rows_per_batch;
+    int32_t channels, ld, index_is64, index_ld;
+};
+
+struct GemmTcParams {
+    int64_t N;
+    int K, Kpad, Cout, Npad;
+    int mode;  // 0 rows, 1 conv3x3
+    int nsrc;
+    GtSrc src[GT_MAX_SRC];
+    int koff[GT_MAX_SRC + 1];
+    int H, W, OH, OW, stride, C;
+    const uint4* wimg;  // hi image then lo image, each [Kpad/8][Npad] uint4
+    const float* scale;
+    const float* shift;
+    const float* residual;
+    int res_ld;
+    int act;
+    float slope;
+    float* out;
+    int out_ld;
+    int out_mode;   // 0 rows, 1 NCHW, 2 deconv pixel shuffle
+    int64_t plane;
+    int ds, dIH, dIW, dC;
+};
+
+__device__ __forceinline__ const float* gt_src_ptr(const GemmTcParams& p, int s, int64_t n) {
+    const GtSrc& S = p.src[s];
+    int64_t r = n;
+    if (S.index) {
+        r = load_index(S.index, n * S.index_ld, S.index_is64);
+        if (r < 0) return nullptr;
+        if (S.out_rows_per_batch > 0) {
+            if (r >= S.src_rows_per_batch) return nullptr;
+            r += (n / S.out_rows_per_batch) * S.src_rows_per_batch;
+        }
+        if (r >= S.rows) return nullptr;
+    }
+    return S.data + (size_t)r * S.ld;
+}
+
+template <int BN>
+struct GtCfg {
+    static constexpr int A_BYTES = GT_CH * GT_ROWS * 16;  // one of hi/lo per stage
+    static constexpr int B_BYTES = GT_CH * BN * 16;
+    static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int B_U4 = 2 * GT_CH * BN;                     // uint4 of B per slice (hi + lo)
+    static constexpr int B_PER_THREAD = (B_U4 + GT_THREADS - 1) / GT_THREADS;
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr size_t SMEM = (size_t)GT_STAGES * STAGE + GT_MAX_SRC * GT_ROWS * 8 + GT_ROWS * 12 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GT_THREADS)
+gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
+    using C = GtCfg<BN>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* stages = smem;
+    const float** rowptr = reinterpret_cast<const float**>(stages + GT_STAGES * C::STAGE);  // [src][row]
+    int* rowinfo = reinterpret_cast<int*>(rowptr + GT_MAX_SRC * GT_ROWS);                   // [row][3]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(rowinfo + GT_ROWS * 3);                    // [STAGES + 1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + GT_STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * GT_ROWS;
+    const int col0 = blockIdx.y * BN;
+
+    // ---- per-row gather bookkeeping
+    if (p.mode == 0) {
+        for (int i = tid; i < p.nsrc * GT_ROWS; i += GT_THREADS) {
+            const int s = i / GT_ROWS, m = i % GT_ROWS;
+            const int64_t n = row0 + m;
+            rowptr[s * GT_ROWS + m] = (n < p.N) ? gt_src_ptr(p, s, n) : nullptr;
+        }
+    } else {
+        for (int m = tid; m < GT_ROWS; m += GT_THREADS) {
+            const int64_t n = row0 + m;
+            if (n < p.N) {
+                const int64_t per = (int64_t)p.OH * p.OW;
+                const int b = (int)(n / per), r = (int)(n % per);
+                rowinfo[m * 3 + 0] = b * p.H * p.W;
+                rowinfo[m * 3 + 1] = (r / p.OW) * p.stride - 1;
+                rowinfo[m * 3 + 2] = (r % p.OW) * p.stride - 1;
+            } else {
+                rowinfo[m * 3 + 0] = -1;
+                rowinfo[m * 3 + 1] = rowinfo[m * 3 + 2] = 0;
+            }
+        }
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i <= GT_STAGES; ++i) tc::mbar_init(&mbar[i], 1);
+        tc::fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == 0) tc::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int nsl = p.Kpad / GT_KS;
+    const size_t img_u4 = (size_t)(p.Kpad / 8) * p.Npad;  // uint4 per image
+    float4 ra[2][2];
+    uint4 rb[C::B_PER_THREAD];
+
+    auto load_regs = [&](int s) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int item = tid + it * GT_THREADS;
+            const int m = item & (GT_ROWS - 1), c = item >> 7;
+            const int k = s * GT_KS + c * 8;
+            const float* src = nullptr;
+            if (k < p.K) {
+                if (p.mode == 1) {
+                    if (rowinfo[m * 3] >= 0) {
+                        const int tap = k / p.C, cc = k - tap * p.C;
+                        const int iy = rowinfo[m * 3 + 1] + tap / 3, ix = rowinfo[m * 3 + 2] + tap % 3;
+                        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                            src = p.src[0].data + ((size_t)rowinfo[m * 3] + (size_t)iy * p.W + ix) * p.C + cc;
+                    }
+                } else {
+                    int sidx = 0;
+                    while (sidx + 1 < p.nsrc && k >= p.koff[sidx + 1]) ++sidx;
+                    const float* base = rowptr[sidx * GT_ROWS + m];
+                    if (base) src = base + (k - p.koff[sidx]);
+                }
+            }
+            if (src) {
+                ra[it][0] = *reinterpret_cast<const float4*>(src);
+                ra[it][1] = *reinterpret_cast<const float4*>(src + 4);
+            } else {
+                ra[it][0] = ra[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < C::B_PER_THREAD; ++j) {
+            const int idx = tid + j * GT_THREADS;
+            if (idx < C::B_U4) {
+                const int img = idx / (GT_CH * BN), rem = idx % (GT_CH * BN);
+                const int cc = rem / BN, r = rem % BN;
+                rb[j] = p.wimg[img * img_u4 + (size_t)(s * GT_CH + cc) * p.Npad + col0 + r];
+            }
+        }
+    };
+    auto store_regs = [&](int stage) {
+        uint8_t* a_hi = stages + (size_t)stage * C::STAGE;
+        uint8_t* a_lo = a_hi + C::A_BYTES;
+        uint4* b = reinterpret_cast<uint4*>(a_lo + C::A_BYTES);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int item = tid + it * GT_THREADS;
+            const int m = item & (GT_ROWS - 1), c = item >> 7;
+            const float x[8] = {ra[it][0].x, ra[it][0].y, ra[it][0].z, ra[it][0].w,
+                                ra[it][1].x, ra[it][1].y, ra[it][1].z, ra[it][1].w};
+            uint4 hi, lo;
+            tc::split8(x, hi, lo);
+            *reinterpret_cast<uint4*>(a_hi + tc::op_off(GT_ROWS, m, c)) = hi;
+            *reinterpret_cast<uint4*>(a_lo + tc::op_off(GT_ROWS, m, c)) = lo;
+        }
+#pragma unroll
+        for (int j = 0; j < C::B_PER_THREAD; ++j) {
+            const int idx = tid + j * GT_THREADS;
+            if (idx < C::B_U4) b[idx] = rb[j];   // [hi: CH x BN][lo: CH x BN] == image order
+        }
+        tc::fence_async_smem();
+    };
+
+    uint32_t ph[GT_STAGES];
+#pragma unroll
+    for (int i = 0; i < GT_STAGES; ++i) ph[i] = 0;
+    load_regs(0);
+    for (int s = 0; s < nsl; ++s) {
+        const int stage = s % GT_STAGES;
+        if (s >= GT_STAGES) {  // the MMAs of slice s - STAGES read this stage
+#pragma unroll
+            for (int i = 0; i < GT_STAGES; ++i)
+                if (i == stage) {
+                    tc::mbar_wait(&mbar[i], ph[i]);
+                    ph[i] ^= 1;
+                }
+        }
+        store_regs(stage);
+        if (s + 1 < nsl) load_regs(s + 1);   // in flight across the barrier and the MMA issue
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        if (tid == 0) {
+            constexpr uint32_t idesc = tc::idesc_f16(GT_ROWS, BN);
+            constexpr uint32_t A_LBO = GT_ROWS * 16, B_LBO = BN * 16;
+            const uint32_t a_hi = tc::smem_u32(stages + (size_t)stage * C::STAGE);
+            const uint32_t a_lo = a_hi + C::A_BYTES;
+            const uint32_t b_hi = a_lo + C::A_BYTES;
+            const uint32_t b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < GT_KS / 16; ++ks) {
+                const uint64_t ah = tc::smem_desc(a_hi + ks * 2 * A_LBO, A_LBO, 128);
+                const uint64_t al = tc::smem_desc(a_lo + ks * 2 * A_LBO, A_LBO, 128);
+                const uint64_t bh = tc::smem_desc(b_hi + ks * 2 * B_LBO, B_LBO, 128);
+                const uint64_t bl = tc::smem_desc(b_lo + ks * 2 * B_LBO, B_LBO, 128);
+                tc::umma_f16(tmem, ah, bh, idesc, (s | ks) > 0);
+                tc::umma_f16(tmem, ah, bl, idesc, 1);
+                tc::umma_f16(tmem, al, bh, idesc, 1);
+            }
+            tc::umma_commit(&mbar[stage]);
+            if (s == nsl - 1) tc::umma_commit(&mbar[GT_STAGES]);
+        }
+    }
+    tc::mbar_wait(&mbar[GT_STAGES], 0);
+    tc::tc_fence_after();
+
+    // ---- epilogue: thread = (row, column half); 16 columns at a time
+    const int row = tid & (GT_ROWS - 1), half = tid >> 7;
+    const int64_t n = row0 + row;
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    for (int c0 = half * 16; c0 < BN; c0 += 32) {
+        float v[16];
+        tc::tmem_ld16(tmem_lane + c0, v);   // warp-collective: every lane takes part
+        const int cbase = col0 + c0;
+        if (n >= p.N || cbase >= p.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = cbase + j;
+            if (c < p.Cout) {
+                float x = v[j];
+                x = fmaf(x, p.scale ? p.scale[c] : 1.f, p.shift ? p.shift[c] : 0.f);
+                if (p.residual) x += p.residual[(size_t)n * p.res_ld + c];
+                v[j] = apply_act(x, p.act, p.slope);
+            }
+        }
+        if (p.out_mode == 0) {
+            float* o = p.out + (size_t)n * p.out_ld + cbase;
+            if (cbase + 15 < p.Cout && (p.out_ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (cbase + j < p.Cout) o[j] = v[j];
+            }
+        } else if (p.out_mode == 1) {
+            const int64_t b = n / p.plane, pix = n % p.plane;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (cbase + j < p.Cout) p.out[((size_t)b * p.Cout + cbase + j) * p.plane + pix] = v[j];
+        } else {
+            const int64_t per = (int64_t)p.dIH * p.dIW;
+            const int64_t b = n / per;
+            const int r = (int)(n % per);
+            const int iy = r / p.dIW, ix = r % p.dIW;
+            const int OWd = p.dIW * p.ds;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int c = cbase + j;
+                if (c < p.Cout) {
+                    const int sub = c / p.dC, co = c - sub * p.dC;
+                    const int dy = sub / p.ds, dx = sub - dy * p.ds;
+                    const size_t opix = ((size_t)b * p.dIH * p.ds + (size_t)iy * p.ds + dy) * OWd +
+                                        (size_t)ix * p.ds + dx;
+                    p.out[opix * p.out_ld + co] = v[j];
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<C::TMEM_COLS>(tmem);
+}
+
+template <int BN>
+static int gemm_tc_launch_bn(const GemmTcParams& p, cudaStream_t st) {
+    using C = GtCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        O3DML_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)C::SMEM));
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div<int64_t>(p.N, GT_ROWS), (unsigned)(p.Npad / BN));
+    gemm_tc_kernel<BN><<<grid, GT_THREADS, C::SMEM, st>>>(p);
+    O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
+    return O3DML_OK;
+}
+
+static int gemm_tc_launch(const GemmTcParams& p, cudaStream_t st) {
+    if (p.N <= 0 || p.Cout <= 0) return O3DML_OK;
+    O3DML_CHECK(p.Kpad % GT_KS == 0 && p.Kpad >= p.K, "linear_tc: weight image K padding must be a multiple of 32");
+    if (p.Npad == 32) return gemm_tc_launch_bn<32>(p, st);
+    if (p.Npad == 64) return gemm_tc_launch_bn<64>(p, st);
+    O3DML_CHECK(p.Npad % 128 == 0, "linear_tc: weight image rows must be padded to 32, 64 or a multiple of 128");
+    return gemm_tc_launch_bn<128>(p, st);
+}
+
+}  // namespace o3dml
+
+using namespace o3dml;
+
+static int gt_common(GemmTcParams& p, const void* wimg, int k_pad, int n_pad, const float* scale,
+                     const float* shift, const float* residual, int residual_ld, int act, float slope,
+                     float* out, int out_ld, int out_channels) {
+    p.wimg = (const uint4*)wimg;
+    p.Kpad = k_pad;
+    p.Npad = n_pad;
+    p.scale = scale; p.shift = shift; p.residual = residual; p.res_ld = residual_ld;
+    p.act = act; p.slope = slope; p.out = out; p.out_ld = out_ld; p.Cout = out_channels;
+    O3DML_CHECK(act >= 0 && act <= 2, "linear_tc: unknown activation %d", act);
+    O3DML_CHECK(wimg && out, "linear_tc: null weight image / out");
+    O3DML_CHECK(n_pad >= out_channels, "linear_tc: weight image has fewer rows than out_channels");
+    return O3DML_OK;
+}
+
+extern "C" int o3dml_linear_tc(int64_t num_rows, const o3dml_src_t* srcs, int num_srcs,
+                               const void* weight_image, int k_pad, int n_pad, const float* scale,
+                               const float* shift, const float* residual, int residual_ld, int act,
+                               float slope, float* out, int out_ld, int out_channels,
+                               int out_nchw_plane, void* stream) {
+    O3DML_CHECK(num_srcs >= 1 && num_srcs <= GT_MAX_SRC, "linear_tc: 1..3 sources");
+    GemmTcParams p = {};
+    p.N = num_rows;
+    p.mode = 0;
+    p.nsrc = num_srcs;
+    int k = 0;
+    for (int s = 0; s < num_srcs; ++s) {
+        const o3dml_src_t& S = srcs[s];
+        O3DML_CHECK(S.data && S.channels > 0 && S.ld >= S.channels, "linear_tc: bad source %d", s);
+        O3DML_CHECK((S.channels & 7) == 0 && (S.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(S.data) & 15) == 0,
+                    "linear_tc: sources need a multiple of 8 channels and 16-byte aligned rows");
+        p.src[s].data = S.data; p.src[s].index = S.index; p.src[s].rows = S.rows;
+        p.src[s].out_rows_per_batch = S.out_rows_per_batch;
+        p.src[s].src_rows_per_batch = S.src_rows_per_batch;
+        p.src[s].channels = S.channels; p.src[s].ld = S.ld; p.src[s].index_is64 = S.index_is64;
+        p.src[s].index_ld = S.index ? (S.index_ld > 0 ? S.index_ld : 1) : 0;
+        p.koff[s] = k;
+        k += S.channels;
+    }
+    for (int s = num_srcs; s <= GT_MAX_SRC; ++s) p.koff[s] = k;
+    p.K = k;
+    int rc = gt_common(p, weight_image, k_pad, n_pad, scale, shift, residual, residual_ld, act, slope, out,
+                       out_ld, out_channels);
+    if (rc) return rc;
+    if (out_nchw_plane > 0) {
+        p.out_mode = 1;
+        p.plane = out_nchw_plane;
+    }
+    return gemm_tc_launch(p, (cudaStream_t)stream);
+}
+
+extern "C" int o3dml_conv3x3_nhwc_tc(const float* in, int batch, int H, int W, int C, int stride,
+                                     const void* weight_image, int k_pad, int n_pad, const float* scale,
+                                     const float* shift, int act, float slope, float* out,
+                                     int out_channels, void* stream) {
+    O3DML_CHECK(in && batch > 0 && H > 0 && W > 0, "conv3x3_tc: bad input");
+    O3DML_CHECK((C % 8) == 0, "conv3x3_tc: input channels must be a multiple of 8");
+    O3DML_CHECK(stride == 1 || stride == 2, "conv3x3_tc: stride 1 or 2");
+    O3DML_CHECK((reinterpret_cast<uintptr_t>(in) & 15) == 0, "conv3x3_tc: input must be 16-byte aligned");
+    GemmTcParams p = {};
+    p.mode = 1;
+    p.nsrc = 1;
+    p.src[0].data = in;
+    p.H = H; p.W = W; p.C = C; p.stride = stride;
+    p.OH = (H + 2 - 3) / stride + 1;
+    p.OW = (W + 2 - 3) / stride + 1;
+    p.N = (int64_t)batch * p.OH * p.OW;
+    p.K = 9 * C;
+    int rc = gt_common(p, weight_image, k_pad, n_pad, scale, shift, nullptr, 0, act, slope, out,
+                       out_channels, out_channels);
+    if (rc) return rc;
+    return gemm_tc_launch(p, (cudaStream_t)stream);
+}
+
+extern "C" int o3dml_deconv_nhwc_tc(const float* in, int batch, int H, int W, int C, int stride,
+                                    const void* weight_image, int k_pad, int n_pad, const float* scale,
+                                    const float* shift, int act, float slope, float* out, int out_ld,
+                                    int out_channels, void* stream) {
+    O3DML_CHECK(in && batch > 0 && H > 0 && W > 0 && stride >= 1, "deconv_tc: bad input");
+    O3DML_CHECK((C % 8) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0, "deconv_tc: C % 8, aligned input");
+    GemmTcParams p = {};
+    p.N = (int64_t)batch * H * W;
+    p.mode = 0;
+    p.nsrc = 1;
+    p.src[0].data = in; p.src[0].rows = p.N; p.src[0].channels = C; p.src[0].ld = C;
+    p.koff[0] = 0;
+    for (int i = 1; i <= GT_MAX_SRC; ++i) p.koff[i] = C;
+    p.K = C;
+    int rc = gt_common(p, weight_image, k_pad, n_pad, scale, shift, nullptr, 0, act, slope, out, out_ld,
+                       stride * stride * out_channels);
+    if (rc) return rc;
+    p.out_mode = 2;
+    p.ds = stride; p.dIH = H; p.dIW = W; p.dC = out_channels;
+    return gemm_tc_launch(p, (cudaStream_t)stream);
+}

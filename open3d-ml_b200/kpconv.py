@@ -83,12 +83,12 @@ class KPFCNNB200:
                 put(p + ".t", sd[p + ".bias"])
 
         def unary(p, use_bn):
-            put(p + ".wt", sd[p + ".mlp.weight"].t())
+            w[p + ".wt"] = L.pack_linear(sd[p + ".mlp.weight"].t())
             bn(p + ".batch_norm", use_bn)
 
         def kpconv(p):
             kw = sd[p + ".weights"]  # [K, Cin, Cout]
-            put(p + ".wt", kw.reshape(kw.shape[0] * kw.shape[1], kw.shape[2]))
+            w[p + ".wt"] = L.pack_linear(kw.reshape(kw.shape[0] * kw.shape[1], kw.shape[2]))
             put(p + ".kp", sd[p + ".kernel_points"])
 
         for bi, b in enumerate(self.enc):

@@ -58,7 +58,7 @@ class PointPillarsB200:
             layers += [("%s.%d" % (p, 3 + 3 * j), "%s.%d" % (p, 4 + 3 * j), 1) for j in range(n)]
             for conv, bn, st in layers:
                 cw = sd[conv + ".weight"]  # [co, ci, 3, 3]
-                put(conv + ".wt", cw.permute(2, 3, 1, 0).reshape(9 * cw.shape[1], cw.shape[0]))
+                w[conv + ".wt"] = L.pack_linear(cw.permute(2, 3, 1, 0).reshape(9 * cw.shape[1], cw.shape[0]))
                 s, t = _fold_bn(sd, bn)
                 put(conv + ".s", s), put(conv + ".t", t)
             self.blocks.append([(c, st, sd[c + ".weight"].shape[1], sd[c + ".weight"].shape[0])
@@ -71,7 +71,7 @@ class PointPillarsB200:
             if dw.shape[2] != us or dw.shape[3] != us:
                 raise RuntimeError("PointPillarsB200: deblock kernel must equal its stride")
             co = dw.shape[1]
-            put(p + ".wt", dw.permute(0, 2, 3, 1).reshape(dw.shape[0], us * us * co))
+            w[p + ".wt"] = L.pack_linear(dw.permute(0, 2, 3, 1).reshape(dw.shape[0], us * us * co))
             s, t = _fold_bn(sd, p + ".1")
             put(p + ".s", s.repeat(us * us)), put(p + ".t", t.repeat(us * us))
             self.deblocks.append((p, us, dw.shape[0], co))
@@ -80,7 +80,7 @@ class PointPillarsB200:
         hw = [sd["bbox_head.%s.weight" % h][:, :, 0, 0] for h in ("conv_cls", "conv_reg", "conv_dir_cls")]
         hb = [sd["bbox_head.%s.bias" % h] for h in ("conv_cls", "conv_reg", "conv_dir_cls")]
         self.head_split = [x.shape[0] for x in hw]
-        put("head.wt", torch.cat(hw, 0).t())
+        w["head.wt"] = L.pack_linear(torch.cat(hw, 0).t())
         put("head.t", torch.cat(hb, 0))
         r = cfg["point_cloud_range"]
         self.vx, self.vy = float(cfg["voxel_size"][0]), float(cfg["voxel_size"][1])
@@ -130,9 +130,16 @@ class PointPillarsB200:
     def _conv(self, x, B, H, W, name, stride, cin, cout):
         OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
         out = self._get(name, (B, OH, OW, cout))
-        L.check(L.lib().o3dml_conv3x3_nhwc(L.ptr(x), B, H, W, cin, stride, L.ptr(self.w[name + ".wt"]),
-                                           L.ptr(self.w[name + ".s"]), L.ptr(self.w[name + ".t"]),
-                                           1, 0.0, L.ptr(out), cout, L.stream()))
+        pw = self.w[name + ".wt"]
+        if L.USE_TC_GEMM and cin % 8 == 0:
+            L.check(L.lib().o3dml_conv3x3_nhwc_tc(L.ptr(x), B, H, W, cin, stride, L.ptr(pw.img), pw.k_pad,
+                                                  pw.n_pad, L.ptr(self.w[name + ".s"]),
+                                                  L.ptr(self.w[name + ".t"]), 1, 0.0, L.ptr(out), cout,
+                                                  L.stream()))
+        else:
+            L.check(L.lib().o3dml_conv3x3_nhwc(L.ptr(x), B, H, W, cin, stride, L.ptr(pw.wt),
+                                               L.ptr(self.w[name + ".s"]), L.ptr(self.w[name + ".t"]),
+                                               1, 0.0, L.ptr(out), cout, L.stream()))
         return out, OH, OW
 
     def backbone_neck_head(self, canvas):
@@ -150,10 +157,17 @@ class PointPillarsB200:
         for (p, us, cin, co), (f, h, w_) in zip(self.deblocks, feats):
             if h * us != OH or w_ * us != OW:
                 raise RuntimeError("PointPillarsB200: neck scales do not line up")
-            L.check(L.lib().o3dml_deconv_nhwc(L.ptr(f), B, h, w_, cin, us, L.ptr(self.w[p + ".wt"]),
-                                              L.ptr(self.w[p + ".s"]), L.ptr(self.w[p + ".t"]), 1, 0.0,
-                                              neck.data_ptr() + 4 * off, self.neck_channels, co,
-                                              L.stream()))
+            pw = self.w[p + ".wt"]
+            if L.USE_TC_GEMM and cin % 8 == 0:
+                L.check(L.lib().o3dml_deconv_nhwc_tc(L.ptr(f), B, h, w_, cin, us, L.ptr(pw.img), pw.k_pad,
+                                                     pw.n_pad, L.ptr(self.w[p + ".s"]), L.ptr(self.w[p + ".t"]),
+                                                     1, 0.0, neck.data_ptr() + 4 * off, self.neck_channels,
+                                                     co, L.stream()))
+            else:
+                L.check(L.lib().o3dml_deconv_nhwc(L.ptr(f), B, h, w_, cin, us, L.ptr(pw.wt),
+                                                  L.ptr(self.w[p + ".s"]), L.ptr(self.w[p + ".t"]), 1, 0.0,
+                                                  neck.data_ptr() + 4 * off, self.neck_channels, co,
+                                                  L.stream()))
             off += co
         ch = sum(self.head_split)
         out = torch.empty((B, ch, OH, OW), dtype=torch.float32, device=self.device)

@@ -49,9 +49,13 @@ class RandLANetB200:
         def put(name, t):
             self.w[name] = t.to(dev, torch.float32).contiguous()
 
-        def shared_mlp(p, transpose=False, bn=True):
+        def shared_mlp(p, transpose=False, bn=True, raw=False):
             w = sd[p + ".conv.weight"][:, :, 0, 0]
-            put(p + ".wt", w if transpose else w.t())
+            w = w if transpose else w.t()
+            if raw:      # consumed by the fused LFA kernels as plain fp32 [in, out]
+                put(p + ".wt", w)
+            else:        # dense layer: fp32 + tensor-core operand image
+                self.w[p + ".wt"] = L.pack_linear(w)
             if bn:
                 s, t = _fold_bn(sd, p + ".batch_norm", sd[p + ".conv.bias"])
                 put(p + ".s", s)
@@ -59,15 +63,15 @@ class RandLANetB200:
             else:
                 put(p + ".t", sd[p + ".conv.bias"])
 
-        put("fc0.wt", sd["fc0.weight"].t())
+        self.w["fc0.wt"] = L.pack_linear(sd["fc0.weight"].t())
         s, t = _fold_bn(sd, "bn0", sd["fc0.bias"])
         put("fc0.s", s), put("fc0.t", t)
         self.d_out = []
         for i in range(num_layers):
             p = "encoder.%d" % i
             shared_mlp(p + ".mlp1")
-            shared_mlp(p + ".lse1.mlp")
-            shared_mlp(p + ".lse2.mlp")
+            shared_mlp(p + ".lse1.mlp", raw=True)
+            shared_mlp(p + ".lse2.mlp", raw=True)
             shared_mlp(p + ".pool1.mlp")
             shared_mlp(p + ".pool2.mlp")
             for pool in ("pool1", "pool2"):
@@ -86,7 +90,7 @@ class RandLANetB200:
             ss, ts = _fold_bn(sd, p + ".shortcut.batch_norm", sd[p + ".shortcut.conv.bias"])
             w2 = sd[p + ".mlp2.conv.weight"][:, :, 0, 0] * s2[:, None]
             ws = sd[p + ".shortcut.conv.weight"][:, :, 0, 0] * ss[:, None]
-            put(p + ".out.wt", torch.cat([w2.t(), ws.t()], 0))
+            self.w[p + ".out.wt"] = L.pack_linear(torch.cat([w2.t(), ws.t()], 0))
             put(p + ".out.t", t2 + ts)
         shared_mlp("mlp")
         for i in range(num_layers):

@@ -25,72 +25,88 @@ def rnd(*shape, seed=0):
     return torch.randn(*shape, generator=g).cuda()
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("n,cin,cout", [(1000, 8, 8), (4099, 3, 8), (777, 32, 19), (5000, 64, 64),
-                                        (300, 768, 256), (2048, 128, 1024), (65, 75, 64), (1, 16, 13)])
-def test_linear_plain(n, cin, cout):
+                                        (300, 768, 256), (2048, 128, 1024), (65, 75, 64), (1, 16, 13),
+                                        (129, 40, 72), (70000, 256, 32)])
+def test_linear_plain(n, cin, cout, tc):
+    """tc=True: PackedWeight -> tcgen05 kernel (gemm_tc.cu) whenever cin % 8 == 0, SIMT otherwise."""
     x, w = rnd(n, cin, seed=1), rnd(cin, cout, seed=2) / cin ** 0.5
     s, t = rnd(cout, seed=3).abs() + 0.5, rnd(cout, seed=4)
-    out = torch.empty(n, cout).cuda()
-    L.linear([L.make_src(x)], w, out, s, t, act="leaky", slope=0.2)
-    ref = F.leaky_relu((x @ w) * s + t, 0.2)
+    out = torch.full((n, cout), float("nan")).cuda()
+    wk = L.pack_linear(w) if tc else w
+    L.linear([L.make_src(x)], wk, out, s, t, act="leaky", slope=0.2)
+    ref = F.leaky_relu((x.double() @ w.double()) * s + t, 0.2)
     assert rel_err(out, ref) < TOL
-    L.linear([L.make_src(x)], w, out, None, None, act=None)
-    assert rel_err(out, x @ w) < TOL
+    L.linear([L.make_src(x)], wk, out, None, None, act=None)
+    assert rel_err(out, x.double() @ w.double()) < TOL
 
 
-def test_linear_concat_gather_residual_batched_index():
+@pytest.mark.parametrize("tc", [False, True])
+def test_linear_concat_gather_residual_batched_index(tc):
     B, nup, nco = 3, 500, 120
     skip, coarse = rnd(B * nup, 32, seed=1), rnd(B * nco, 64, seed=2)
     idx = torch.randint(0, nco, (B, nup, 1), generator=torch.Generator().manual_seed(3)).cuda()
     w, t, res = rnd(96, 48, seed=4) / 10, rnd(48, seed=5), rnd(B * nup, 48, seed=6)
     out = torch.empty(B * nup, 48).cuda()
     L.linear([L.make_src(skip), L.make_src(coarse, index=idx.view(-1), out_rows_per_batch=nup,
-                                           src_rows_per_batch=nco)], w, out, None, t, residual=res, act="relu")
+                                           src_rows_per_batch=nco)], L.pack_linear(w) if tc else w, out, None, t,
+             residual=res, act="relu")
     up = torch.gather(coarse.view(B, nco, 64), 1, idx.expand(-1, -1, 64)).reshape(B * nup, 64)
     ref = torch.relu(torch.cat([skip, up], 1) @ w + t + res)
     assert rel_err(out, ref) < TOL
     # global int32 index with shadow rows (== rows -> zeros), column 0 of a wider index matrix
     nq, ns = 700, 300
-    x = rnd(ns, 20, seed=7)
+    x = rnd(ns, 24 if tc else 20, seed=7)
     nb = torch.randint(0, ns + 1, (nq, 5), generator=torch.Generator().manual_seed(8)).to(torch.int32).cuda()
-    w2 = rnd(20, 7, seed=9)
+    w2 = rnd(x.shape[1], 7, seed=9)
     out2 = torch.empty(nq, 7).cuda()
-    L.linear([L.make_src(x, index=nb, index_ld=5)], w2, out2, act=None)
-    xz = torch.cat([x, torch.zeros(1, 20).cuda()])
+    L.linear([L.make_src(x, index=nb, index_ld=5)], L.pack_linear(w2) if tc else w2, out2, act=None)
+    xz = torch.cat([x, torch.zeros(1, x.shape[1]).cuda()])
     assert rel_err(out2, xz[nb[:, 0].long()] @ w2) < TOL
 
 
-def test_linear_nchw_output_and_strided_out():
+@pytest.mark.parametrize("tc", [False, True])
+def test_linear_nchw_output_and_strided_out(tc):
     B, H, W, C, Co = 2, 9, 7, 24, 10
     x, w, b = rnd(B * H * W, C, seed=1), rnd(C, Co, seed=2), rnd(Co, seed=3)
     out = torch.empty(B, Co, H, W).cuda()
-    L.linear([L.make_src(x)], w, out, None, b, act=None, num_rows=B * H * W, out_channels=Co, out_nchw_plane=H * W)
+    L.linear([L.make_src(x)], L.pack_linear(w) if tc else w, out, None, b, act=None, num_rows=B * H * W,
+             out_channels=Co, out_nchw_plane=H * W)
     ref = (x @ w + b).view(B, H * W, Co).permute(0, 2, 1).reshape(B, Co, H, W)
     assert rel_err(out, ref) < TOL
     wide = torch.zeros(B * H * W, 40).cuda()                 # write 12 channels into columns 16..28
     w3 = rnd(C, 12, seed=4)
-    L.linear([L.make_src(x)], w3, wide[:, 16:28], act=None, num_rows=B * H * W, out_ld=40)
+    L.linear([L.make_src(x)], L.pack_linear(w3) if tc else w3, wide[:, 16:28], act=None, num_rows=B * H * W,
+             out_ld=40)
     assert rel_err(wide[:, 16:28], x @ w3) < TOL and float(wide[:, :16].abs().max()) == 0 and float(wide[:, 28:].abs().max()) == 0
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("B,H,W,C,Co,stride", [(1, 20, 16, 64, 64, 1), (2, 31, 27, 64, 128, 2),
                                                 (1, 62, 54, 128, 128, 1), (1, 13, 13, 256, 256, 2)])
-def test_conv3x3_nhwc(B, H, W, C, Co, stride):
+def test_conv3x3_nhwc(B, H, W, C, Co, stride, tc):
     x = rnd(B, H, W, C, seed=1)
     w = rnd(Co, C, 3, 3, seed=2) / (9 * C) ** 0.5
     s, t = rnd(Co, seed=3).abs() + 0.5, rnd(Co, seed=4)
     OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
     out = torch.empty(B, OH, OW, Co).cuda()
     wt = w.permute(2, 3, 1, 0).reshape(9 * C, Co).contiguous()
-    L.check(L.lib().o3dml_conv3x3_nhwc(L.ptr(x), B, H, W, C, stride, L.ptr(wt), L.ptr(s), L.ptr(t), 1, 0.0,
-                                       L.ptr(out), Co, L.stream()))
+    if tc:
+        pw = L.pack_linear(wt)
+        L.check(L.lib().o3dml_conv3x3_nhwc_tc(L.ptr(x), B, H, W, C, stride, L.ptr(pw.img), pw.k_pad, pw.n_pad,
+                                              L.ptr(s), L.ptr(t), 1, 0.0, L.ptr(out), Co, L.stream()))
+    else:
+        L.check(L.lib().o3dml_conv3x3_nhwc(L.ptr(x), B, H, W, C, stride, L.ptr(wt), L.ptr(s), L.ptr(t), 1, 0.0,
+                                           L.ptr(out), Co, L.stream()))
     ref = F.conv2d(x.permute(0, 3, 1, 2), w, None, stride, 1)
     ref = torch.relu(ref * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
     assert ref.shape == out.shape and rel_err(out, ref) < TOL
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("stride", [1, 2, 4])
-def test_deconv_nhwc_into_concat_buffer(stride):
+def test_deconv_nhwc_into_concat_buffer(stride, tc):
     B, H, W, C, Co = 2, 6, 5, 64, 128
     x = rnd(B, H, W, C, seed=1)
     w = rnd(C, Co, stride, stride, seed=2) / C ** 0.5
@@ -98,8 +114,14 @@ def test_deconv_nhwc_into_concat_buffer(stride):
     neck = torch.zeros(B, H * stride, W * stride, 384).cuda()
     wt = w.permute(0, 2, 3, 1).reshape(C, stride * stride * Co).contiguous()
     s_rep, t_rep = s.repeat(stride * stride), t.repeat(stride * stride)   # keep alive across the call
-    L.check(L.lib().o3dml_deconv_nhwc(L.ptr(x), B, H, W, C, stride, L.ptr(wt), L.ptr(s_rep), L.ptr(t_rep), 1, 0.0,
-                                      neck.data_ptr() + 4 * 128, 384, Co, L.stream()))
+    if tc:
+        pw = L.pack_linear(wt)
+        L.check(L.lib().o3dml_deconv_nhwc_tc(L.ptr(x), B, H, W, C, stride, L.ptr(pw.img), pw.k_pad, pw.n_pad,
+                                             L.ptr(s_rep), L.ptr(t_rep), 1, 0.0, neck.data_ptr() + 4 * 128, 384,
+                                             Co, L.stream()))
+    else:
+        L.check(L.lib().o3dml_deconv_nhwc(L.ptr(x), B, H, W, C, stride, L.ptr(wt), L.ptr(s_rep), L.ptr(t_rep), 1,
+                                          0.0, neck.data_ptr() + 4 * 128, 384, Co, L.stream()))
     ref = F.conv_transpose2d(x.permute(0, 3, 1, 2), w, None, stride)
     ref = torch.relu(ref * s.view(1, -1, 1, 1) + t.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
     assert rel_err(neck[..., 128:256], ref) < TOL
