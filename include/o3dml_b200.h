@@ -162,19 +162,23 @@ O3DML_API int o3dml_deconv_nhwc(const float* in, int batch, int H, int W, int C,
 
 /* Tensor-core (tcgen05, 3xFP16 split) variants of the three dense entry points above.  Instead of
  * weight_t they take the host-packed fp16 hi/lo operand image of the weight [n_pad][k_pad]
- * (zero padded; k_pad % 32 == 0; n_pad in {32, 64, 128*j}; open3d_ml_b200._lib.pack_linear).
- * Every source needs a multiple of 8 channels. */
+ * (zero padded; k_pad % 32 == 0; n_pad in {32, 64, 128*j}; open3d_ml_b200._lib.pack_linear), holding
+ * weight * 2^weight_exp (power-of-two range normalisation, undone in the epilogue together with the
+ * per-CTA normalisation of the gathered A tile).  Every source needs a multiple of 8 channels. */
 O3DML_API int o3dml_linear_tc(int64_t num_rows, const o3dml_src_t* srcs, int num_srcs,
-                              const void* weight_image, int k_pad, int n_pad, const float* scale,
+                              const void* weight_image, int k_pad, int n_pad, int weight_exp,
+                              const float* scale,
                               const float* shift, const float* residual, int residual_ld, int act,
                               float slope, float* out, int out_ld, int out_channels,
                               int out_nchw_plane, void* stream);
 O3DML_API int o3dml_conv3x3_nhwc_tc(const float* in, int batch, int H, int W, int C, int stride,
-                                    const void* weight_image, int k_pad, int n_pad, const float* scale,
+                                    const void* weight_image, int k_pad, int n_pad, int weight_exp,
+                              const float* scale,
                                     const float* shift, int act, float slope, float* out,
                                     int out_channels, void* stream);
 O3DML_API int o3dml_deconv_nhwc_tc(const float* in, int batch, int H, int W, int C, int stride,
-                                   const void* weight_image, int k_pad, int n_pad, const float* scale,
+                                   const void* weight_image, int k_pad, int n_pad, int weight_exp,
+                              const float* scale,
                                    const float* shift, int act, float slope, float* out, int out_ld,
                                    int out_channels, void* stream);
 

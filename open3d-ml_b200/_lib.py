@@ -4,6 +4,7 @@ There is NO CPU fallback: every entry point needs the CUDA library and a CUDA
 device, and fails loudly otherwise.
 """
 import ctypes
+import math
 import os
 
 import torch
@@ -42,9 +43,9 @@ _SIGNATURES = {
     "o3dml_linear": (I, [L, ctypes.POINTER(Src), I, P, P, P, P, I, I, F, P, I, I, I, P]),
     "o3dml_conv3x3_nhwc": (I, [P, I, I, I, I, I, P, P, P, I, F, P, I, P]),
     "o3dml_deconv_nhwc": (I, [P, I, I, I, I, I, P, P, P, I, F, P, I, I, P]),
-    "o3dml_linear_tc": (I, [L, ctypes.POINTER(Src), I, P, I, I, P, P, P, I, I, F, P, I, I, I, P]),
-    "o3dml_conv3x3_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, P, P, I, F, P, I, P]),
-    "o3dml_deconv_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, P, P, I, F, P, I, I, P]),
+    "o3dml_linear_tc": (I, [L, ctypes.POINTER(Src), I, P, I, I, I, P, P, P, I, I, F, P, I, I, I, P]),
+    "o3dml_conv3x3_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, I, P, P, I, F, P, I, P]),
+    "o3dml_deconv_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, I, P, P, I, F, P, I, I, P]),
     "o3dml_randla_lfa_pool": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
     "o3dml_randla_lfa_pool_tc": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
     "o3dml_gather_max": (I, [P, L, I, I, P, I, L, I, L, L, I, P, I, P]),
@@ -129,8 +130,12 @@ class PackedWeight:
         self.wt = w.cuda()
         self.k_pad = (self.k + 31) // 32 * 32
         self.n_pad = 32 if self.cout <= 32 else 64 if self.cout <= 64 else (self.cout + 127) // 128 * 128
+        wmax = float(w.abs().max())
+        # power-of-two range normalisation: max |w| * 2^w_exp in [2^13, 2^14) keeps the fp16 lo parts normal
+        self.w_exp = int(13 - math.floor(math.log2(wmax))) if 0.0 < wmax < 3.0e38 else 0
+        self.w_exp = max(-100, min(100, self.w_exp))
         wp = torch.zeros((self.n_pad, self.k_pad), dtype=torch.float32)
-        wp[:self.cout, :self.k] = w.t()
+        wp[:self.cout, :self.k] = w.t() * (2.0 ** self.w_exp)
         self.img = pack_operand_image(wp)
 
     @property
@@ -159,7 +164,7 @@ def linear(srcs, weight, out, scale=None, shift=None, residual=None, act=None, s
     ld = (out.stride(0) if out_nchw_plane == 0 else co) if out_ld is None else out_ld
     res_ld = residual.stride(0) if residual is not None else 0
     if packed and _tc_ok(srcs):
-        check(lib().o3dml_linear_tc(n, arr, len(srcs), ptr(weight.img), weight.k_pad, weight.n_pad,
+        check(lib().o3dml_linear_tc(n, arr, len(srcs), ptr(weight.img), weight.k_pad, weight.n_pad, weight.w_exp,
                                     ptr(scale), ptr(shift), ptr(residual), res_ld, act_code(act),
                                     float(slope), ptr(out), ld, co, out_nchw_plane, stream()))
     else:

@@ -7,6 +7,10 @@
 //   * B comes from a host-packed hi/lo operand image ([K/8][Cout_pad][8 halves], zero padded),
 //   * the accumulator [128 x BN] lives in TMEM; a 3-stage ring lets the conversion of slice s+1
 //     overlap the MMAs of slice s (global loads of slice s+1 are in flight across the barrier).
+// fp16 has a narrow exponent range (the lo parts go subnormal for |x| < 0.125 and precision
+// decays to 1e-4 for |x| ~ 1e-4), so every CTA first takes the max |A| of its own tile (one extra
+// pass over data that is read again right after, i.e. L2 hits) and rescales by an exact power of two
+// to [2^13, 2^14); the weight image is normalised the same way by the host; the epilogue undoes both.
 // Serves SharedMLP / UnaryBlock / KPConv [15*Cin, Cout] / SECOND + FPN + head convolutions whenever
 // every source has a multiple of 8 channels; the FP32 SIMT kernel (gemm.cu) takes the rest.
 #include "../../include/o3dml_b200.h"
@@ -38,6 +42,7 @@ struct GemmTcParams {
     int koff[GT_MAX_SRC + 1];
     int H, W, OH, OW, stride, C;
     const uint4* wimg;  // hi image then lo image, each [Kpad/8][Npad] uint4
+    int wexp;           // the image holds weight * 2^wexp (host-side range normalisation)
     const float* scale;
     const float* shift;
     const float* residual;
@@ -130,29 +135,62 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     const size_t img_u4 = (size_t)(p.Kpad / 8) * p.Npad;  // uint4 per image
     float4 ra[2][2];
     uint4 rb[C::B_PER_THREAD];
+    __shared__ unsigned amax_warp[GT_THREADS / 32];
+    float a_scale = 1.f, out_scale = 1.f;
 
+    auto a_src = [&](int s, int it) -> const float* {
+        const int item = tid + it * GT_THREADS;
+        const int m = item & (GT_ROWS - 1), c = item >> 7;
+        const int k = s * GT_KS + c * 8;
+        const float* src = nullptr;
+        if (k < p.K) {
+            if (p.mode == 1) {
+                if (rowinfo[m * 3] >= 0) {
+                    const int tap = k / p.C, cc = k - tap * p.C;
+                    const int iy = rowinfo[m * 3 + 1] + tap / 3, ix = rowinfo[m * 3 + 2] + tap % 3;
+                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+                        src = p.src[0].data + ((size_t)rowinfo[m * 3] + (size_t)iy * p.W + ix) * p.C + cc;
+                }
+            } else {
+                int sidx = 0;
+                while (sidx + 1 < p.nsrc && k >= p.koff[sidx + 1]) ++sidx;
+                const float* base = rowptr[sidx * GT_ROWS + m];
+                if (base) src = base + (k - p.koff[sidx]);
+            }
+        }
+        return src;
+    };
+    {   // ---- range pass: max |A| over this CTA's tile -> exact power-of-two scale
+        float mx = 0.f;
+        for (int s = 0; s < nsl; ++s) {
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const float* src = a_src(s, it);
+                if (src) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(src);
+                    const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
+                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
+                }
+            }
+        }
+        const unsigned wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));  // mx >= 0: bits are ordered
+        if ((tid & 31) == 0) amax_warp[warp] = wmx;
+        __syncthreads();
+        unsigned bm = 0;
+#pragma unroll
+        for (int i = 0; i < GT_THREADS / 32; ++i) bm = max(bm, amax_warp[i]);
+        const float amax = __uint_as_float(bm);
+        int e = 0;
+        if (amax > 0.f && amax < 3.0e38f) e = 13 - ilogbf(amax);   // amax * 2^e in [2^13, 2^14)
+        e = max(-100, min(100, e));
+        a_scale = ldexpf(1.f, e);
+        out_scale = ldexpf(1.f, -e - p.wexp);
+    }
     auto load_regs = [&](int s) {
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-            const int item = tid + it * GT_THREADS;
-            const int m = item & (GT_ROWS - 1), c = item >> 7;
-            const int k = s * GT_KS + c * 8;
-            const float* src = nullptr;
-            if (k < p.K) {
-                if (p.mode == 1) {
-                    if (rowinfo[m * 3] >= 0) {
-                        const int tap = k / p.C, cc = k - tap * p.C;
-                        const int iy = rowinfo[m * 3 + 1] + tap / 3, ix = rowinfo[m * 3 + 2] + tap % 3;
-                        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-                            src = p.src[0].data + ((size_t)rowinfo[m * 3] + (size_t)iy * p.W + ix) * p.C + cc;
-                    }
-                } else {
-                    int sidx = 0;
-                    while (sidx + 1 < p.nsrc && k >= p.koff[sidx + 1]) ++sidx;
-                    const float* base = rowptr[sidx * GT_ROWS + m];
-                    if (base) src = base + (k - p.koff[sidx]);
-                }
-            }
+            const float* src = a_src(s, it);
             if (src) {
                 ra[it][0] = *reinterpret_cast<const float4*>(src);
                 ra[it][1] = *reinterpret_cast<const float4*>(src + 4);
@@ -178,8 +216,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         for (int it = 0; it < 2; ++it) {
             const int item = tid + it * GT_THREADS;
             const int m = item & (GT_ROWS - 1), c = item >> 7;
-            const float x[8] = {ra[it][0].x, ra[it][0].y, ra[it][0].z, ra[it][0].w,
-                                ra[it][1].x, ra[it][1].y, ra[it][1].z, ra[it][1].w};
+            const float x[8] = {ra[it][0].x * a_scale, ra[it][0].y * a_scale, ra[it][0].z * a_scale,
+                                ra[it][0].w * a_scale, ra[it][1].x * a_scale, ra[it][1].y * a_scale,
+                                ra[it][1].z * a_scale, ra[it][1].w * a_scale};
             uint4 hi, lo;
             tc::split8(x, hi, lo);
             *reinterpret_cast<uint4*>(a_hi + tc::op_off(GT_ROWS, m, c)) = hi;
@@ -249,7 +288,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         for (int j = 0; j < 16; ++j) {
             const int c = cbase + j;
             if (c < p.Cout) {
-                float x = v[j];
+                float x = v[j] * out_scale;   // exact: undoes the two power-of-two range scalings
                 x = fmaf(x, p.scale ? p.scale[c] : 1.f, p.shift ? p.shift[c] : 0.f);
                 if (p.residual) x += p.residual[(size_t)n * p.res_ld + c];
                 v[j] = apply_act(x, p.act, p.slope);
@@ -324,12 +363,13 @@ static int gemm_tc_launch(const GemmTcParams& p, cudaStream_t st) {
 
 using namespace o3dml;
 
-static int gt_common(GemmTcParams& p, const void* wimg, int k_pad, int n_pad, const float* scale,
+static int gt_common(GemmTcParams& p, const void* wimg, int k_pad, int n_pad, int w_exp, const float* scale,
                      const float* shift, const float* residual, int residual_ld, int act, float slope,
                      float* out, int out_ld, int out_channels) {
     p.wimg = (const uint4*)wimg;
     p.Kpad = k_pad;
     p.Npad = n_pad;
+    p.wexp = w_exp;
     p.scale = scale; p.shift = shift; p.residual = residual; p.res_ld = residual_ld;
     p.act = act; p.slope = slope; p.out = out; p.out_ld = out_ld; p.Cout = out_channels;
     O3DML_CHECK(act >= 0 && act <= 2, "linear_tc: unknown activation %d", act);
@@ -339,7 +379,8 @@ static int gt_common(GemmTcParams& p, const void* wimg, int k_pad, int n_pad, co
 }
 
 extern "C" int o3dml_linear_tc(int64_t num_rows, const o3dml_src_t* srcs, int num_srcs,
-                               const void* weight_image, int k_pad, int n_pad, const float* scale,
+                               const void* weight_image, int k_pad, int n_pad, int weight_exp,
+                               const float* scale,
                                const float* shift, const float* residual, int residual_ld, int act,
                                float slope, float* out, int out_ld, int out_channels,
                                int out_nchw_plane, void* stream) {
@@ -364,7 +405,7 @@ extern "C" int o3dml_linear_tc(int64_t num_rows, const o3dml_src_t* srcs, int nu
     }
     for (int s = num_srcs; s <= GT_MAX_SRC; ++s) p.koff[s] = k;
     p.K = k;
-    int rc = gt_common(p, weight_image, k_pad, n_pad, scale, shift, residual, residual_ld, act, slope, out,
+    int rc = gt_common(p, weight_image, k_pad, n_pad, weight_exp, scale, shift, residual, residual_ld, act, slope, out,
                        out_ld, out_channels);
     if (rc) return rc;
     if (out_nchw_plane > 0) {
@@ -375,7 +416,8 @@ extern "C" int o3dml_linear_tc(int64_t num_rows, const o3dml_src_t* srcs, int nu
 }
 
 extern "C" int o3dml_conv3x3_nhwc_tc(const float* in, int batch, int H, int W, int C, int stride,
-                                     const void* weight_image, int k_pad, int n_pad, const float* scale,
+                                     const void* weight_image, int k_pad, int n_pad, int weight_exp,
+                               const float* scale,
                                      const float* shift, int act, float slope, float* out,
                                      int out_channels, void* stream) {
     O3DML_CHECK(in && batch > 0 && H > 0 && W > 0, "conv3x3_tc: bad input");
@@ -391,14 +433,15 @@ extern "C" int o3dml_conv3x3_nhwc_tc(const float* in, int batch, int H, int W, i
     p.OW = (W + 2 - 3) / stride + 1;
     p.N = (int64_t)batch * p.OH * p.OW;
     p.K = 9 * C;
-    int rc = gt_common(p, weight_image, k_pad, n_pad, scale, shift, nullptr, 0, act, slope, out,
+    int rc = gt_common(p, weight_image, k_pad, n_pad, weight_exp, scale, shift, nullptr, 0, act, slope, out,
                        out_channels, out_channels);
     if (rc) return rc;
     return gemm_tc_launch(p, (cudaStream_t)stream);
 }
 
 extern "C" int o3dml_deconv_nhwc_tc(const float* in, int batch, int H, int W, int C, int stride,
-                                    const void* weight_image, int k_pad, int n_pad, const float* scale,
+                                    const void* weight_image, int k_pad, int n_pad, int weight_exp,
+                               const float* scale,
                                     const float* shift, int act, float slope, float* out, int out_ld,
                                     int out_channels, void* stream) {
     O3DML_CHECK(in && batch > 0 && H > 0 && W > 0 && stride >= 1, "deconv_tc: bad input");
@@ -411,7 +454,7 @@ extern "C" int o3dml_deconv_nhwc_tc(const float* in, int batch, int H, int W, in
     p.koff[0] = 0;
     for (int i = 1; i <= GT_MAX_SRC; ++i) p.koff[i] = C;
     p.K = C;
-    int rc = gt_common(p, weight_image, k_pad, n_pad, scale, shift, nullptr, 0, act, slope, out, out_ld,
+    int rc = gt_common(p, weight_image, k_pad, n_pad, weight_exp, scale, shift, nullptr, 0, act, slope, out, out_ld,
                        stride * stride * out_channels);
     if (rc) return rc;
     p.out_mode = 2;

@@ -94,7 +94,7 @@ def test_conv3x3_nhwc(B, H, W, C, Co, stride, tc):
     wt = w.permute(2, 3, 1, 0).reshape(9 * C, Co).contiguous()
     if tc:
         pw = L.pack_linear(wt)
-        L.check(L.lib().o3dml_conv3x3_nhwc_tc(L.ptr(x), B, H, W, C, stride, L.ptr(pw.img), pw.k_pad, pw.n_pad,
+        L.check(L.lib().o3dml_conv3x3_nhwc_tc(L.ptr(x), B, H, W, C, stride, L.ptr(pw.img), pw.k_pad, pw.n_pad, pw.w_exp,
                                               L.ptr(s), L.ptr(t), 1, 0.0, L.ptr(out), Co, L.stream()))
     else:
         L.check(L.lib().o3dml_conv3x3_nhwc(L.ptr(x), B, H, W, C, stride, L.ptr(wt), L.ptr(s), L.ptr(t), 1, 0.0,
@@ -116,7 +116,7 @@ def test_deconv_nhwc_into_concat_buffer(stride, tc):
     s_rep, t_rep = s.repeat(stride * stride), t.repeat(stride * stride)   # keep alive across the call
     if tc:
         pw = L.pack_linear(wt)
-        L.check(L.lib().o3dml_deconv_nhwc_tc(L.ptr(x), B, H, W, C, stride, L.ptr(pw.img), pw.k_pad, pw.n_pad,
+        L.check(L.lib().o3dml_deconv_nhwc_tc(L.ptr(x), B, H, W, C, stride, L.ptr(pw.img), pw.k_pad, pw.n_pad, pw.w_exp,
                                              L.ptr(s_rep), L.ptr(t_rep), 1, 0.0, neck.data_ptr() + 4 * 128, 384,
                                              Co, L.stream()))
     else:
@@ -161,3 +161,14 @@ def test_kpconv_gather_vs_torch(cin, H):
     w = torch.eye(K * cin).view(K, cin, K * cin).cuda()      # identity weights expose the [K*Cin] tensor
     ref = MT.kp_conv(q_pts, s_pts, nb, x, kp, w, ext)
     assert rel_err(a, ref) < TOL
+
+
+@pytest.mark.parametrize("mag", [1e-6, 1e-3, 1.0, 3e4])
+def test_linear_tc_is_magnitude_independent(mag):
+    """fp16 split operands are range-normalised per CTA tile (gemm_tc.cu): the relative error must not
+    depend on the scale of the activations (without normalisation it is 1.7e-4 at |x| ~ 1e-4)."""
+    n, cin, cout = 3000, 256, 64
+    x, w = rnd(n, cin, seed=1) * mag, rnd(cin, cout, seed=2) * 1e-3
+    out = torch.empty(n, cout).cuda()
+    L.linear([L.make_src(x)], L.pack_linear(w), out, act=None)
+    assert rel_err(out, x.double() @ w.double()) < 2e-6
