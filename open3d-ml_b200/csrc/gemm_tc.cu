@@ -24,6 +24,7 @@ constexpr int GT_ROWS = 128;
 constexpr int GT_KS = 32;       // channels per k-slice
 constexpr int GT_CH = GT_KS / 8;
 constexpr int GT_STAGES = 3;
+constexpr int GT_FLUSH = 8;      // k-slices (256 channels) per TMEM accumulation chunk
 constexpr int GT_MAX_SRC = 3;
 
 struct GtSrc {
@@ -71,6 +72,18 @@ __device__ __forceinline__ const float* gt_src_ptr(const GemmTcParams& p, int s,
     return S.data + (size_t)r * S.ld;
 }
 
+// ---- cp.async (16-byte, zero-fill when src_bytes == 0) -----------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 template <int BN>
 struct GtCfg {
     static constexpr int A_BYTES = GT_CH * GT_ROWS * 16;  // one of hi/lo per stage
@@ -78,20 +91,30 @@ struct GtCfg {
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int B_U4 = 2 * GT_CH * BN;                     // uint4 of B per slice (hi + lo)
     static constexpr int B_PER_THREAD = (B_U4 + GT_THREADS - 1) / GT_THREADS;
-    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // two accumulator buffers
     static constexpr size_t SMEM = (size_t)GT_STAGES * STAGE + GT_MAX_SRC * GT_ROWS * 8 + GT_ROWS * 12 + 256;
 };
 
+// Pipeline (per CTA, one [128 x BN] output tile, k-slices of 32 channels through a GT_STAGES ring):
+//   cp.async   raw fp32 A pieces are parked IN the slots where their fp16 hi / lo words will live
+//              (floats 0-3 of a (row, 8-channel chunk) in the hi slot, floats 4-7 in the lo slot), the
+//              weight image slices go straight to their final place; GT_STAGES-1 slices are in flight
+//   convert    each thread rewrites its own two 16-byte slots in place: x*2^e -> (hi, lo) halves
+//   MMA        one thread issues 3 x 2 tcgen05.mma per slice; its commit frees the stage
+//   flush      every GT_FLUSH slices the TMEM accumulator is added (RN) into registers and the next
+//              chunk starts a fresh accumulator in the other TMEM buffer: the tensor core adds with
+//              truncation (measured -3e-8 relative per accumulation, -5e-5 at K = 7680 otherwise)
 template <int BN>
-__global__ void __launch_bounds__(GT_THREADS)
+__global__ void __launch_bounds__(GT_THREADS, 2)
 gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     using C = GtCfg<BN>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stages = smem;
     const float** rowptr = reinterpret_cast<const float**>(stages + GT_STAGES * C::STAGE);  // [src][row]
     int* rowinfo = reinterpret_cast<int*>(rowptr + GT_MAX_SRC * GT_ROWS);                   // [row][3]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(rowinfo + GT_ROWS * 3);                    // [STAGES + 1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + GT_STAGES + 1);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(rowinfo + GT_ROWS * 3);   // [STAGES] stage free, [2] chunk done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + GT_STAGES + 2);
+    __shared__ unsigned amax_warp[GT_THREADS / 32];
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int64_t row0 = (int64_t)blockIdx.x * GT_ROWS;
@@ -121,7 +144,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     }
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i <= GT_STAGES; ++i) tc::mbar_init(&mbar[i], 1);
+        for (int i = 0; i < GT_STAGES + 2; ++i) tc::mbar_init(&mbar[i], 1);
         tc::fence_mbar_init();
     }
     __syncthreads();
@@ -133,10 +156,6 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 
     const int nsl = p.Kpad / GT_KS;
     const size_t img_u4 = (size_t)(p.Kpad / 8) * p.Npad;  // uint4 per image
-    float4 ra[2][2];
-    uint4 rb[C::B_PER_THREAD];
-    __shared__ unsigned amax_warp[GT_THREADS / 32];
-    float a_scale = 1.f, out_scale = 1.f;
 
     auto a_src = [&](int s, int it) -> const float* {
         const int item = tid + it * GT_THREADS;
@@ -160,6 +179,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         }
         return src;
     };
+
+    float a_scale, out_scale;
     {   // ---- range pass: max |A| over this CTA's tile -> exact power-of-two scale
         float mx = 0.f;
         for (int s = 0; s < nsl; ++s) {
@@ -187,16 +208,21 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         a_scale = ldexpf(1.f, e);
         out_scale = ldexpf(1.f, -e - p.wexp);
     }
-    auto load_regs = [&](int s) {
+
+    // ---- producers
+    auto issue_loads = [&](int s) {   // cp.async of k-slice s into ring stage s % GT_STAGES
+        uint8_t* a_hi = stages + (size_t)(s % GT_STAGES) * C::STAGE;
+        uint8_t* a_lo = a_hi + C::A_BYTES;
+        uint4* b = reinterpret_cast<uint4*>(a_lo + C::A_BYTES);
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
+            const int item = tid + it * GT_THREADS;
+            const int m = item & (GT_ROWS - 1), c = item >> 7;
             const float* src = a_src(s, it);
-            if (src) {
-                ra[it][0] = *reinterpret_cast<const float4*>(src);
-                ra[it][1] = *reinterpret_cast<const float4*>(src + 4);
-            } else {
-                ra[it][0] = ra[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            const void* g0 = src ? (const void*)src : (const void*)p.wimg;
+            const void* g1 = src ? (const void*)(src + 4) : (const void*)p.wimg;
+            cp_async16(a_hi + tc::op_off(GT_ROWS, m, c), g0, src ? 16 : 0);
+            cp_async16(a_lo + tc::op_off(GT_ROWS, m, c), g1, src ? 16 : 0);
         }
 #pragma unroll
         for (int j = 0; j < C::B_PER_THREAD; ++j) {
@@ -204,52 +230,67 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             if (idx < C::B_U4) {
                 const int img = idx / (GT_CH * BN), rem = idx % (GT_CH * BN);
                 const int cc = rem / BN, r = rem % BN;
-                rb[j] = p.wimg[img * img_u4 + (size_t)(s * GT_CH + cc) * p.Npad + col0 + r];
+                cp_async16(&b[idx], &p.wimg[img * img_u4 + (size_t)(s * GT_CH + cc) * p.Npad + col0 + r], 16);
             }
         }
     };
-    auto store_regs = [&](int stage) {
-        uint8_t* a_hi = stages + (size_t)stage * C::STAGE;
+    auto convert = [&](int s) {       // this thread's own raw pieces -> fp16 hi / lo, in place
+        uint8_t* a_hi = stages + (size_t)(s % GT_STAGES) * C::STAGE;
         uint8_t* a_lo = a_hi + C::A_BYTES;
-        uint4* b = reinterpret_cast<uint4*>(a_lo + C::A_BYTES);
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
             const int item = tid + it * GT_THREADS;
             const int m = item & (GT_ROWS - 1), c = item >> 7;
-            const float x[8] = {ra[it][0].x * a_scale, ra[it][0].y * a_scale, ra[it][0].z * a_scale,
-                                ra[it][0].w * a_scale, ra[it][1].x * a_scale, ra[it][1].y * a_scale,
-                                ra[it][1].z * a_scale, ra[it][1].w * a_scale};
+            uint4* ph = reinterpret_cast<uint4*>(a_hi + tc::op_off(GT_ROWS, m, c));
+            uint4* pl = reinterpret_cast<uint4*>(a_lo + tc::op_off(GT_ROWS, m, c));
+            const float4 v0 = *reinterpret_cast<const float4*>(ph);
+            const float4 v1 = *reinterpret_cast<const float4*>(pl);
+            const float x[8] = {v0.x * a_scale, v0.y * a_scale, v0.z * a_scale, v0.w * a_scale,
+                                v1.x * a_scale, v1.y * a_scale, v1.z * a_scale, v1.w * a_scale};
             uint4 hi, lo;
             tc::split8(x, hi, lo);
-            *reinterpret_cast<uint4*>(a_hi + tc::op_off(GT_ROWS, m, c)) = hi;
-            *reinterpret_cast<uint4*>(a_lo + tc::op_off(GT_ROWS, m, c)) = lo;
-        }
-#pragma unroll
-        for (int j = 0; j < C::B_PER_THREAD; ++j) {
-            const int idx = tid + j * GT_THREADS;
-            if (idx < C::B_U4) b[idx] = rb[j];   // [hi: CH x BN][lo: CH x BN] == image order
+            *ph = hi;
+            *pl = lo;
         }
         tc::fence_async_smem();
     };
 
-    uint32_t ph[GT_STAGES];
+    // ---- accumulator flush state: thread = (row, column half)
+    const int half = tid >> 7;
+    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    constexpr int NACC = BN >= 32 ? BN / 2 : 16;
+    float racc[NACC];
 #pragma unroll
-    for (int i = 0; i < GT_STAGES; ++i) ph[i] = 0;
-    load_regs(0);
+    for (int i = 0; i < NACC; ++i) racc[i] = 0.f;
+    auto flush = [&](int buf) {       // racc += TMEM accumulator buffer `buf` (round to nearest)
+#pragma unroll
+        for (int q = 0; q < BN / 32; ++q) {
+            const int c0 = half * 16 + 32 * q;
+            float v[16];
+            tc::tmem_ld16(tmem_lane + buf * BN + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) racc[q * 16 + j] += v[j];
+        }
+    };
+
+    uint32_t ph_stage[GT_STAGES], ph_chunk[2] = {0, 0};
+#pragma unroll
+    for (int i = 0; i < GT_STAGES; ++i) ph_stage[i] = 0;
+
+    // prologue: GT_STAGES - 1 slices in flight (empty commit groups keep the group count uniform)
+#pragma unroll
+    for (int s = 0; s < GT_STAGES - 1; ++s) {
+        if (s < nsl) issue_loads(s);
+        cp_async_commit();
+    }
+    int pending_chunk = -1;   // chunk whose accumulator still has to be flushed into racc
     for (int s = 0; s < nsl; ++s) {
         const int stage = s % GT_STAGES;
-        if (s >= GT_STAGES) {  // the MMAs of slice s - STAGES read this stage
-#pragma unroll
-            for (int i = 0; i < GT_STAGES; ++i)
-                if (i == stage) {
-                    tc::mbar_wait(&mbar[i], ph[i]);
-                    ph[i] ^= 1;
-                }
-        }
-        store_regs(stage);
-        if (s + 1 < nsl) load_regs(s + 1);   // in flight across the barrier and the MMA issue
+        const int chunk = s / GT_FLUSH;
+        cp_async_wait<GT_STAGES - 2>();          // this thread's pieces of slice s have landed
+        convert(s);
         tc::tc_fence_before();
-        __syncthreads();
+        __syncthreads();                          // every piece of slice s (A converted, B copied) is visible
         tc::tc_fence_after();
         if (tid == 0) {
             constexpr uint32_t idesc = tc::idesc_f16(GT_ROWS, BN);
@@ -258,37 +299,72 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             const uint32_t a_lo = a_hi + C::A_BYTES;
             const uint32_t b_hi = a_lo + C::A_BYTES;
             const uint32_t b_lo = b_hi + C::B_BYTES;
+            const uint32_t acc = tmem + (uint32_t)((chunk & 1) * BN);
+            const bool first = (s % GT_FLUSH) == 0;
 #pragma unroll
             for (int ks = 0; ks < GT_KS / 16; ++ks) {
                 const uint64_t ah = tc::smem_desc(a_hi + ks * 2 * A_LBO, A_LBO, 128);
                 const uint64_t al = tc::smem_desc(a_lo + ks * 2 * A_LBO, A_LBO, 128);
                 const uint64_t bh = tc::smem_desc(b_hi + ks * 2 * B_LBO, B_LBO, 128);
                 const uint64_t bl = tc::smem_desc(b_lo + ks * 2 * B_LBO, B_LBO, 128);
-                tc::umma_f16(tmem, ah, bh, idesc, (s | ks) > 0);
-                tc::umma_f16(tmem, ah, bl, idesc, 1);
-                tc::umma_f16(tmem, al, bh, idesc, 1);
+                tc::umma_f16(acc, ah, bh, idesc, !(first && ks == 0));
+                tc::umma_f16(acc, ah, bl, idesc, 1);
+                tc::umma_f16(acc, al, bh, idesc, 1);
             }
             tc::umma_commit(&mbar[stage]);
-            if (s == nsl - 1) tc::umma_commit(&mbar[GT_STAGES]);
+            if ((s % GT_FLUSH) == GT_FLUSH - 1 || s == nsl - 1) tc::umma_commit(&mbar[GT_STAGES + (chunk & 1)]);
         }
+        // a chunk that finished one slice ago has certainly drained: fold it into the registers
+        if (pending_chunk >= 0) {
+            tc::mbar_wait(&mbar[GT_STAGES + (pending_chunk & 1)], ph_chunk[pending_chunk & 1]);
+            ph_chunk[pending_chunk & 1] ^= 1;
+            tc::tc_fence_after();
+            flush(pending_chunk & 1);
+            pending_chunk = -1;
+        }
+        if ((s % GT_FLUSH) == GT_FLUSH - 1 && s != nsl - 1) pending_chunk = chunk;
+        // refill the stage that slice s-1 used (its MMAs were issued one iteration ago)
+        const int sn = s + GT_STAGES - 1;
+        if (sn < nsl) {
+            if (s >= 1) {
+                const int st = (s - 1) % GT_STAGES;
+#pragma unroll
+                for (int i = 0; i < GT_STAGES; ++i)
+                    if (i == st) {
+                        tc::mbar_wait(&mbar[i], ph_stage[i]);
+                        ph_stage[i] ^= 1;
+                    }
+            }
+            issue_loads(sn);
+        }
+        cp_async_commit();
     }
-    tc::mbar_wait(&mbar[GT_STAGES], 0);
+    // ---- last chunk
+    const int last_chunk = (nsl - 1) / GT_FLUSH;
+    if (pending_chunk >= 0) {   // only when the final chunk has a single slice: flush the one before it
+        tc::mbar_wait(&mbar[GT_STAGES + (pending_chunk & 1)], ph_chunk[pending_chunk & 1]);
+        ph_chunk[pending_chunk & 1] ^= 1;
+        tc::tc_fence_after();
+        flush(pending_chunk & 1);
+    }
+    tc::mbar_wait(&mbar[GT_STAGES + (last_chunk & 1)], ph_chunk[last_chunk & 1]);
     tc::tc_fence_after();
 
     // ---- epilogue: thread = (row, column half); 16 columns at a time
-    const int row = tid & (GT_ROWS - 1), half = tid >> 7;
+    const int row = tid & (GT_ROWS - 1);
     const int64_t n = row0 + row;
-    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    for (int c0 = half * 16; c0 < BN; c0 += 32) {
+#pragma unroll
+    for (int q = 0; q < BN / 32; ++q) {
+        const int c0 = half * 16 + 32 * q;
         float v[16];
-        tc::tmem_ld16(tmem_lane + c0, v);   // warp-collective: every lane takes part
+        tc::tmem_ld16(tmem_lane + (last_chunk & 1) * BN + c0, v);   // warp-collective: every lane takes part
         const int cbase = col0 + c0;
         if (n >= p.N || cbase >= p.Cout) continue;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int c = cbase + j;
             if (c < p.Cout) {
-                float x = v[j] * out_scale;   // exact: undoes the two power-of-two range scalings
+                float x = (v[j] + racc[q * 16 + j]) * out_scale;   // exact: undoes the power-of-two scalings
                 x = fmaf(x, p.scale ? p.scale[c] : 1.f, p.shift ? p.shift[c] : 0.f);
                 if (p.residual) x += p.residual[(size_t)n * p.res_ld + c];
                 v[j] = apply_act(x, p.act, p.slope);
@@ -298,8 +374,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             float* o = p.out + (size_t)n * p.out_ld + cbase;
             if (cbase + 15 < p.Cout && (p.out_ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    *reinterpret_cast<float4*>(o + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int u = 0; u < 4; ++u)
+                    *reinterpret_cast<float4*>(o + 4 * u) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
