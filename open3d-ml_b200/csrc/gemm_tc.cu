@@ -157,44 +157,77 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     const int nsl = p.Kpad / GT_KS;
     const size_t img_u4 = (size_t)(p.Kpad / 8) * p.Npad;  // uint4 per image
 
-    auto a_src = [&](int s, int it) -> const float* {
+    // ---- per-thread gather state.  The two (row, 8-channel chunk) items of a thread are the same in
+    // every slice, so everything that does not depend on the slice index is resolved here once.
+    int it_m[2], it_c[2];
+    const float* it_base[2];      // conv: pixel (iy0, ix0) of the row, rows mode with one source: the row
+    unsigned it_taps[2];          // conv: bit t set when tap t lies inside the image
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
         const int item = tid + it * GT_THREADS;
-        const int m = item & (GT_ROWS - 1), c = item >> 7;
-        const int k = s * GT_KS + c * 8;
-        const float* src = nullptr;
-        if (k < p.K) {
-            if (p.mode == 1) {
-                if (rowinfo[m * 3] >= 0) {
-                    const int tap = k / p.C, cc = k - tap * p.C;
-                    const int iy = rowinfo[m * 3 + 1] + tap / 3, ix = rowinfo[m * 3 + 2] + tap % 3;
-                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
-                        src = p.src[0].data + ((size_t)rowinfo[m * 3] + (size_t)iy * p.W + ix) * p.C + cc;
+        it_m[it] = item & (GT_ROWS - 1);
+        it_c[it] = item >> 7;
+        it_base[it] = nullptr;
+        it_taps[it] = 0;
+        const int m = it_m[it];
+        if (p.mode == 1) {
+            if (rowinfo[m * 3] >= 0) {
+                const int iy0 = rowinfo[m * 3 + 1], ix0 = rowinfo[m * 3 + 2];
+                it_base[it] = p.src[0].data + ((int64_t)rowinfo[m * 3] + (int64_t)iy0 * p.W + ix0) * p.C;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int iy = iy0 + t / 3, ix = ix0 + t % 3;
+                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) it_taps[it] |= 1u << t;
                 }
-            } else {
-                int sidx = 0;
-                while (sidx + 1 < p.nsrc && k >= p.koff[sidx + 1]) ++sidx;
-                const float* base = rowptr[sidx * GT_ROWS + m];
-                if (base) src = base + (k - p.koff[sidx]);
             }
+        } else if (p.nsrc == 1) {
+            it_base[it] = rowptr[m];
         }
-        return src;
+    }
+    const bool conv_fast = p.mode == 1 && (p.C % GT_KS) == 0;   // a 32-channel slice never straddles taps
+    const int slices_per_tap = conv_fast ? p.C / GT_KS : 1;
+    auto a_src = [&](int s, int it) -> const float* {
+        const int m = it_m[it], c = it_c[it];
+        const int k = s * GT_KS + c * 8;
+        if (k >= p.K) return nullptr;
+        if (p.mode == 1) {
+            int tap, cc;
+            if (conv_fast) {
+                tap = s / slices_per_tap;
+                cc = (s - tap * slices_per_tap) * GT_KS + c * 8;
+            } else {
+                tap = k / p.C;
+                cc = k - tap * p.C;
+            }
+            if (!((it_taps[it] >> tap) & 1u)) return nullptr;
+            return it_base[it] + ((int64_t)(tap / 3) * p.W + (tap % 3)) * p.C + cc;
+        }
+        if (p.nsrc == 1) return it_base[it] ? it_base[it] + k : nullptr;
+        int sidx = 0;
+        while (sidx + 1 < p.nsrc && k >= p.koff[sidx + 1]) ++sidx;
+        const float* base = rowptr[sidx * GT_ROWS + m];
+        return base ? base + (k - p.koff[sidx]) : nullptr;
     };
 
     float a_scale, out_scale;
     {   // ---- range pass: max |A| over this CTA's tile -> exact power-of-two scale
-        float mx = 0.f;
-        for (int s = 0; s < nsl; ++s) {
+        float mx4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int s0 = 0; s0 < nsl; s0 += 4) {
 #pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const float* src = a_src(s, it);
-                if (src) {
-                    const float4 v0 = *reinterpret_cast<const float4*>(src);
-                    const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
-                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
-                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
+            for (int u = 0; u < 4; ++u) {       // four slices in flight: independent loads and maxima
+#pragma unroll
+                for (int it = 0; it < 2; ++it) {
+                    const float* src = (s0 + u < nsl) ? a_src(s0 + u, it) : nullptr;
+                    if (src) {
+                        const float4 v0 = *reinterpret_cast<const float4*>(src);
+                        const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+                        mx4[u] = fmaxf(mx4[u], fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
+                        mx4[u] = fmaxf(mx4[u], fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
+                    }
                 }
             }
         }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         const unsigned wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));  // mx >= 0: bits are ordered
         if ((tid & 31) == 0) amax_warp[warp] = wmx;
         __syncthreads();
@@ -210,28 +243,31 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     }
 
     // ---- producers
+    const uint4* b_src[C::B_PER_THREAD];   // this thread's weight-image words of slice 0
+#pragma unroll
+    for (int j = 0; j < C::B_PER_THREAD; ++j) {
+        const int idx = tid + j * GT_THREADS;
+        const int img = idx / (GT_CH * BN), rem = idx % (GT_CH * BN);
+        b_src[j] = p.wimg + img * img_u4 + (size_t)(rem / BN) * p.Npad + col0 + (rem % BN);
+    }
+    const size_t b_step = (size_t)GT_CH * p.Npad;   // uint4 between consecutive slices
     auto issue_loads = [&](int s) {   // cp.async of k-slice s into ring stage s % GT_STAGES
         uint8_t* a_hi = stages + (size_t)(s % GT_STAGES) * C::STAGE;
         uint8_t* a_lo = a_hi + C::A_BYTES;
         uint4* b = reinterpret_cast<uint4*>(a_lo + C::A_BYTES);
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-            const int item = tid + it * GT_THREADS;
-            const int m = item & (GT_ROWS - 1), c = item >> 7;
             const float* src = a_src(s, it);
             const void* g0 = src ? (const void*)src : (const void*)p.wimg;
             const void* g1 = src ? (const void*)(src + 4) : (const void*)p.wimg;
-            cp_async16(a_hi + tc::op_off(GT_ROWS, m, c), g0, src ? 16 : 0);
-            cp_async16(a_lo + tc::op_off(GT_ROWS, m, c), g1, src ? 16 : 0);
+            const uint32_t off = tc::op_off(GT_ROWS, it_m[it], it_c[it]);
+            cp_async16(a_hi + off, g0, src ? 16 : 0);
+            cp_async16(a_lo + off, g1, src ? 16 : 0);
         }
 #pragma unroll
         for (int j = 0; j < C::B_PER_THREAD; ++j) {
             const int idx = tid + j * GT_THREADS;
-            if (idx < C::B_U4) {
-                const int img = idx / (GT_CH * BN), rem = idx % (GT_CH * BN);
-                const int cc = rem / BN, r = rem % BN;
-                cp_async16(&b[idx], &p.wimg[img * img_u4 + (size_t)(s * GT_CH + cc) * p.Npad + col0 + r], 16);
-            }
+            if (idx < C::B_U4) cp_async16(&b[idx], b_src[j] + (size_t)s * b_step, 16);
         }
     };
     auto convert = [&](int s) {       // this thread's own raw pieces -> fp16 hi / lo, in place
@@ -239,10 +275,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         uint8_t* a_lo = a_hi + C::A_BYTES;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-            const int item = tid + it * GT_THREADS;
-            const int m = item & (GT_ROWS - 1), c = item >> 7;
-            uint4* ph = reinterpret_cast<uint4*>(a_hi + tc::op_off(GT_ROWS, m, c));
-            uint4* pl = reinterpret_cast<uint4*>(a_lo + tc::op_off(GT_ROWS, m, c));
+            const uint32_t off = tc::op_off(GT_ROWS, it_m[it], it_c[it]);
+            uint4* ph = reinterpret_cast<uint4*>(a_hi + off);
+            uint4* pl = reinterpret_cast<uint4*>(a_lo + off);
             const float4 v0 = *reinterpret_cast<const float4*>(ph);
             const float4 v1 = *reinterpret_cast<const float4*>(pl);
             const float x[8] = {v0.x * a_scale, v0.y * a_scale, v0.z * a_scale, v0.w * a_scale,
