@@ -86,7 +86,10 @@ __device__ __forceinline__ void cp_async_wait() {
 
 template <int BN>
 struct GtCfg {
-    static constexpr int A_BYTES = GT_CH * GT_ROWS * 16;  // one of hi/lo per stage
+    // chunk stride of the A operand padded by 16 B (UMMA LBO is free): lanes that differ in the chunk
+    // index hit different banks when they convert their slots in place
+    static constexpr int A_LBO = GT_ROWS * 16 + 16;
+    static constexpr int A_BYTES = GT_CH * A_LBO;         // one of hi/lo per stage
     static constexpr int B_BYTES = GT_CH * BN * 16;
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int B_U4 = 2 * GT_CH * BN;                     // uint4 of B per slice (hi + lo)
@@ -165,8 +168,8 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const int item = tid + it * GT_THREADS;
-        it_m[it] = item & (GT_ROWS - 1);
-        it_c[it] = item >> 7;
+        it_m[it] = item >> 2;          // 4 consecutive lanes read the 4 x 32 B of one row's 128-byte slice:
+        it_c[it] = item & 3;           // 8 cache lines per warp request instead of 32
         it_base[it] = nullptr;
         it_taps[it] = 0;
         const int m = it_m[it];
@@ -260,7 +263,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             const float* src = a_src(s, it);
             const void* g0 = src ? (const void*)src : (const void*)p.wimg;
             const void* g1 = src ? (const void*)(src + 4) : (const void*)p.wimg;
-            const uint32_t off = tc::op_off(GT_ROWS, it_m[it], it_c[it]);
+            const uint32_t off = (uint32_t)it_c[it] * C::A_LBO + (uint32_t)it_m[it] * 16u;
             cp_async16(a_hi + off, g0, src ? 16 : 0);
             cp_async16(a_lo + off, g1, src ? 16 : 0);
         }
@@ -275,7 +278,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         uint8_t* a_lo = a_hi + C::A_BYTES;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
-            const uint32_t off = tc::op_off(GT_ROWS, it_m[it], it_c[it]);
+            const uint32_t off = (uint32_t)it_c[it] * C::A_LBO + (uint32_t)it_m[it] * 16u;
             uint4* ph = reinterpret_cast<uint4*>(a_hi + off);
             uint4* pl = reinterpret_cast<uint4*>(a_lo + off);
             const float4 v0 = *reinterpret_cast<const float4*>(ph);
@@ -329,7 +332,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         tc::tc_fence_after();
         if (tid == 0) {
             constexpr uint32_t idesc = tc::idesc_f16(GT_ROWS, BN);
-            constexpr uint32_t A_LBO = GT_ROWS * 16, B_LBO = BN * 16;
+            constexpr uint32_t A_LBO = C::A_LBO, B_LBO = BN * 16;
             const uint32_t a_hi = tc::smem_u32(stages + (size_t)stage * C::STAGE);
             const uint32_t a_lo = a_hi + C::A_BYTES;
             const uint32_t b_hi = a_lo + C::A_BYTES;
