@@ -23,7 +23,7 @@ constexpr int GT_THREADS = 256;
 constexpr int GT_ROWS = 128;
 constexpr int GT_KS = 32;       // channels per k-slice
 constexpr int GT_CH = GT_KS / 8;
-constexpr int GT_STAGES = 3;
+constexpr int GT_STAGES = 5;
 constexpr int GT_FLUSH = 8;      // k-slices (256 channels) per TMEM accumulation chunk
 constexpr int GT_MAX_SRC = 3;
 
@@ -83,6 +83,13 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+// the mbarrier gets one arrival from this thread once all of its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 template <int BN>
 struct GtCfg {
@@ -108,15 +115,15 @@ struct GtCfg {
 //              chunk starts a fresh accumulator in the other TMEM buffer: the tensor core adds with
 //              truncation (measured -3e-8 relative per accumulation, -5e-5 at K = 7680 otherwise)
 template <int BN>
-__global__ void __launch_bounds__(GT_THREADS, 2)
+__global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     using C = GtCfg<BN>;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* stages = smem;
     const float** rowptr = reinterpret_cast<const float**>(stages + GT_STAGES * C::STAGE);  // [src][row]
     int* rowinfo = reinterpret_cast<int*>(rowptr + GT_MAX_SRC * GT_ROWS);                   // [row][3]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(rowinfo + GT_ROWS * 3);   // [STAGES] stage free, [2] chunk done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + GT_STAGES + 2);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(rowinfo + GT_ROWS * 3);   // full[S], empty[S], chunk[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * GT_STAGES + 2);
     __shared__ unsigned amax_warp[GT_THREADS / 32];
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -147,7 +154,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     }
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < GT_STAGES + 2; ++i) tc::mbar_init(&mbar[i], 1);
+        for (int i = 0; i < GT_STAGES; ++i) tc::mbar_init(&mbar[i], GT_THREADS / 2);        // full: loaders
+#pragma unroll
+        for (int i = GT_STAGES; i < 2 * GT_STAGES + 2; ++i) tc::mbar_init(&mbar[i], 1);       // empty, chunk
         tc::fence_mbar_init();
     }
     __syncthreads();
@@ -245,155 +254,188 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         out_scale = ldexpf(1.f, -e - p.wexp);
     }
 
-    // ---- producers
-    const uint4* b_src[C::B_PER_THREAD];   // this thread's weight-image words of slice 0
-#pragma unroll
-    for (int j = 0; j < C::B_PER_THREAD; ++j) {
-        const int idx = tid + j * GT_THREADS;
-        const int img = idx / (GT_CH * BN), rem = idx % (GT_CH * BN);
-        b_src[j] = p.wimg + img * img_u4 + (size_t)(rem / BN) * p.Npad + col0 + (rem % BN);
-    }
-    const size_t b_step = (size_t)GT_CH * p.Npad;   // uint4 between consecutive slices
-    auto issue_loads = [&](int s) {   // cp.async of k-slice s into ring stage s % GT_STAGES
-        uint8_t* a_hi = stages + (size_t)(s % GT_STAGES) * C::STAGE;
-        uint8_t* a_lo = a_hi + C::A_BYTES;
-        uint4* b = reinterpret_cast<uint4*>(a_lo + C::A_BYTES);
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const float* src = a_src(s, it);
-            const void* g0 = src ? (const void*)src : (const void*)p.wimg;
-            const void* g1 = src ? (const void*)(src + 4) : (const void*)p.wimg;
-            const uint32_t off = (uint32_t)it_c[it] * C::A_LBO + (uint32_t)it_m[it] * 16u;
-            cp_async16(a_hi + off, g0, src ? 16 : 0);
-            cp_async16(a_lo + off, g1, src ? 16 : 0);
-        }
-#pragma unroll
-        for (int j = 0; j < C::B_PER_THREAD; ++j) {
-            const int idx = tid + j * GT_THREADS;
-            if (idx < C::B_U4) cp_async16(&b[idx], b_src[j] + (size_t)s * b_step, 16);
-        }
-    };
-    auto convert = [&](int s) {       // this thread's own raw pieces -> fp16 hi / lo, in place
-        uint8_t* a_hi = stages + (size_t)(s % GT_STAGES) * C::STAGE;
-        uint8_t* a_lo = a_hi + C::A_BYTES;
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const uint32_t off = (uint32_t)it_c[it] * C::A_LBO + (uint32_t)it_m[it] * 16u;
-            uint4* ph = reinterpret_cast<uint4*>(a_hi + off);
-            uint4* pl = reinterpret_cast<uint4*>(a_lo + off);
-            const float4 v0 = *reinterpret_cast<const float4*>(ph);
-            const float4 v1 = *reinterpret_cast<const float4*>(pl);
-            const float x[8] = {v0.x * a_scale, v0.y * a_scale, v0.z * a_scale, v0.w * a_scale,
-                                v1.x * a_scale, v1.y * a_scale, v1.z * a_scale, v1.w * a_scale};
-            uint4 hi, lo;
-            tc::split8(x, hi, lo);
-            *ph = hi;
-            *pl = lo;
-        }
-        tc::fence_async_smem();
-    };
-
-    // ---- accumulator flush state: thread = (row, column half)
-    const int half = tid >> 7;
+    // ---- warp-specialised pipeline.  Warps 0-3 only LOAD (cp.async, completion signalled through
+    // full[stage] by cp.async.mbarrier.arrive); warps 4-7 CONVERT in place, fence, and one of their
+    // threads issues the MMAs whose commit frees the stage (empty[stage]).  Keeping the two roles in
+    // different threads matters: fence.proxy.async drains the issuing thread's outstanding cp.async,
+    // so a thread that both prefetches and fences never has a load in flight across the fence
+    // (measured: 2.5 us per k-slice regardless of the prefetch depth).
+    uint64_t* full_bar = mbar;                       // [GT_STAGES], 128 loader arrivals
+    uint64_t* empty_bar = mbar + GT_STAGES;          // [GT_STAGES], tcgen05.commit
+    uint64_t* chunk_bar = mbar + 2 * GT_STAGES;      // [2]
+    constexpr int HALF = GT_THREADS / 2;
+    const bool is_loader = tid < HALF;
+    const int rt = tid & (HALF - 1);                 // thread index inside its role
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    constexpr int NACC = BN >= 32 ? BN / 2 : 16;
-    float racc[NACC];
+    float racc[BN];                                  // converters: RN-accumulated chunk sums of their row
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) racc[i] = 0.f;
-    auto flush = [&](int buf) {       // racc += TMEM accumulator buffer `buf` (round to nearest)
-#pragma unroll
-        for (int q = 0; q < BN / 32; ++q) {
-            const int c0 = half * 16 + 32 * q;
-            float v[16];
-            tc::tmem_ld16(tmem_lane + buf * BN + c0, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) racc[q * 16 + j] += v[j];
-        }
-    };
-
-    uint32_t ph_stage[GT_STAGES], ph_chunk[2] = {0, 0};
-#pragma unroll
-    for (int i = 0; i < GT_STAGES; ++i) ph_stage[i] = 0;
-
-    // prologue: GT_STAGES - 1 slices in flight (empty commit groups keep the group count uniform)
-#pragma unroll
-    for (int s = 0; s < GT_STAGES - 1; ++s) {
-        if (s < nsl) issue_loads(s);
-        cp_async_commit();
-    }
-    int pending_chunk = -1;   // chunk whose accumulator still has to be flushed into racc
-    for (int s = 0; s < nsl; ++s) {
-        const int stage = s % GT_STAGES;
-        const int chunk = s / GT_FLUSH;
-        cp_async_wait<GT_STAGES - 2>();          // this thread's pieces of slice s have landed
-        convert(s);
-        tc::tc_fence_before();
-        __syncthreads();                          // every piece of slice s (A converted, B copied) is visible
-        tc::tc_fence_after();
-        if (tid == 0) {
-            constexpr uint32_t idesc = tc::idesc_f16(GT_ROWS, BN);
-            constexpr uint32_t A_LBO = C::A_LBO, B_LBO = BN * 16;
-            const uint32_t a_hi = tc::smem_u32(stages + (size_t)stage * C::STAGE);
-            const uint32_t a_lo = a_hi + C::A_BYTES;
-            const uint32_t b_hi = a_lo + C::A_BYTES;
-            const uint32_t b_lo = b_hi + C::B_BYTES;
-            const uint32_t acc = tmem + (uint32_t)((chunk & 1) * BN);
-            const bool first = (s % GT_FLUSH) == 0;
-#pragma unroll
-            for (int ks = 0; ks < GT_KS / 16; ++ks) {
-                const uint64_t ah = tc::smem_desc(a_hi + ks * 2 * A_LBO, A_LBO, 128);
-                const uint64_t al = tc::smem_desc(a_lo + ks * 2 * A_LBO, A_LBO, 128);
-                const uint64_t bh = tc::smem_desc(b_hi + ks * 2 * B_LBO, B_LBO, 128);
-                const uint64_t bl = tc::smem_desc(b_lo + ks * 2 * B_LBO, B_LBO, 128);
-                tc::umma_f16(acc, ah, bh, idesc, !(first && ks == 0));
-                tc::umma_f16(acc, ah, bl, idesc, 1);
-                tc::umma_f16(acc, al, bh, idesc, 1);
-            }
-            tc::umma_commit(&mbar[stage]);
-            if ((s % GT_FLUSH) == GT_FLUSH - 1 || s == nsl - 1) tc::umma_commit(&mbar[GT_STAGES + (chunk & 1)]);
-        }
-        // a chunk that finished one slice ago has certainly drained: fold it into the registers
-        if (pending_chunk >= 0) {
-            tc::mbar_wait(&mbar[GT_STAGES + (pending_chunk & 1)], ph_chunk[pending_chunk & 1]);
-            ph_chunk[pending_chunk & 1] ^= 1;
-            tc::tc_fence_after();
-            flush(pending_chunk & 1);
-            pending_chunk = -1;
-        }
-        if ((s % GT_FLUSH) == GT_FLUSH - 1 && s != nsl - 1) pending_chunk = chunk;
-        // refill the stage that slice s-1 used (its MMAs were issued one iteration ago)
-        const int sn = s + GT_STAGES - 1;
-        if (sn < nsl) {
-            if (s >= 1) {
-                const int st = (s - 1) % GT_STAGES;
-#pragma unroll
-                for (int i = 0; i < GT_STAGES; ++i)
-                    if (i == st) {
-                        tc::mbar_wait(&mbar[i], ph_stage[i]);
-                        ph_stage[i] ^= 1;
-                    }
-            }
-            issue_loads(sn);
-        }
-        cp_async_commit();
-    }
-    // ---- last chunk
+    for (int i = 0; i < BN; ++i) racc[i] = 0.f;
     const int last_chunk = (nsl - 1) / GT_FLUSH;
-    if (pending_chunk >= 0) {   // only when the final chunk has a single slice: flush the one before it
-        tc::mbar_wait(&mbar[GT_STAGES + (pending_chunk & 1)], ph_chunk[pending_chunk & 1]);
-        ph_chunk[pending_chunk & 1] ^= 1;
-        tc::tc_fence_after();
-        flush(pending_chunk & 1);
-    }
-    tc::mbar_wait(&mbar[GT_STAGES + (last_chunk & 1)], ph_chunk[last_chunk & 1]);
-    tc::tc_fence_after();
 
-    // ---- epilogue: thread = (row, column half); 16 columns at a time
-    const int row = tid & (GT_ROWS - 1);
+    if (is_loader) {
+        // ------------------------------------------------------------------ loaders
+        int lm[4], lc[4];
+        const float* lbase[4];
+        unsigned ltaps[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                // 512 (row, chunk) items, 4 per loader thread
+            const int item = rt + j * HALF;
+            lm[j] = item >> 2;
+            lc[j] = item & 3;
+            lbase[j] = nullptr;
+            ltaps[j] = 0;
+            const int m = lm[j];
+            if (p.mode == 1) {
+                if (rowinfo[m * 3] >= 0) {
+                    const int iy0 = rowinfo[m * 3 + 1], ix0 = rowinfo[m * 3 + 2];
+                    lbase[j] = p.src[0].data + ((int64_t)rowinfo[m * 3] + (int64_t)iy0 * p.W + ix0) * p.C;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const int iy = iy0 + t / 3, ix = ix0 + t % 3;
+                        if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) ltaps[j] |= 1u << t;
+                    }
+                }
+            } else if (p.nsrc == 1) {
+                lbase[j] = rowptr[m];
+            }
+        }
+        constexpr int LB = (C::B_U4 + HALF - 1) / HALF;   // weight-image words per loader thread
+        const uint4* b_src[LB];
+#pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const int idx = rt + j * HALF;
+            const int img = idx / (GT_CH * BN), rem = idx % (GT_CH * BN);
+            b_src[j] = p.wimg + img * img_u4 + (size_t)(rem / BN) * p.Npad + col0 + (rem % BN);
+        }
+        const size_t b_step = (size_t)GT_CH * p.Npad;
+        for (int s = 0; s < nsl; ++s) {
+            const int stage = s % GT_STAGES, use = s / GT_STAGES;
+            if (use >= 1) tc::mbar_wait(&empty_bar[stage], (use - 1) & 1);   // MMAs of slice s-STAGES done
+            uint8_t* a_hi = stages + (size_t)stage * C::STAGE;
+            uint8_t* a_lo = a_hi + C::A_BYTES;
+            uint4* bdst = reinterpret_cast<uint4*>(a_lo + C::A_BYTES);
+            int tap = 0, cc0 = s * GT_KS;
+            if (p.mode == 1) {
+                if (conv_fast) {
+                    tap = s / slices_per_tap;
+                    cc0 = (s - tap * slices_per_tap) * GT_KS;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = s * GT_KS + lc[j] * 8;
+                const float* src = nullptr;
+                if (k < p.K) {
+                    if (p.mode == 1) {
+                        int t = tap, cc = cc0 + lc[j] * 8;
+                        if (!conv_fast) {
+                            t = k / p.C;
+                            cc = k - t * p.C;
+                        }
+                        if ((ltaps[j] >> t) & 1u) src = lbase[j] + ((int64_t)(t / 3) * p.W + (t % 3)) * p.C + cc;
+                    } else if (p.nsrc == 1) {
+                        if (lbase[j]) src = lbase[j] + k;
+                    } else {
+                        int sidx = 0;
+                        while (sidx + 1 < p.nsrc && k >= p.koff[sidx + 1]) ++sidx;
+                        const float* base = rowptr[sidx * GT_ROWS + lm[j]];
+                        if (base) src = base + (k - p.koff[sidx]);
+                    }
+                }
+                const void* g0 = src ? (const void*)src : (const void*)p.wimg;
+                const void* g1 = src ? (const void*)(src + 4) : (const void*)p.wimg;
+                const uint32_t off = (uint32_t)lc[j] * C::A_LBO + (uint32_t)lm[j] * 16u;
+                cp_async16(a_hi + off, g0, src ? 16 : 0);
+                cp_async16(a_lo + off, g1, src ? 16 : 0);
+            }
+#pragma unroll
+            for (int j = 0; j < LB; ++j) {
+                const int idx = rt + j * HALF;
+                if (idx < C::B_U4) cp_async16(&bdst[idx], b_src[j] + (size_t)s * b_step, 16);
+            }
+            cp_async_arrive(&full_bar[stage]);
+        }
+        cp_async_wait<0>();
+    } else {
+        // ---------------------------------------------------------------- converters + MMA + flush
+        auto flush = [&](int buf) {       // racc += TMEM accumulator buffer `buf` (round to nearest)
+#pragma unroll
+            for (int q = 0; q < BN / 16; ++q) {
+                float v[16];
+                tc::tmem_ld16(tmem_lane + buf * BN + q * 16, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) racc[q * 16 + j] += v[j];
+            }
+        };
+        uint32_t ph_chunk[2] = {0, 0};
+        int pending_chunk = -1;
+        for (int s = 0; s < nsl; ++s) {
+            const int stage = s % GT_STAGES, use = s / GT_STAGES;
+            const int chunk = s / GT_FLUSH;
+            tc::mbar_wait(&full_bar[stage], use & 1);        // every piece of slice s has landed
+            uint8_t* a_hi = stages + (size_t)stage * C::STAGE;
+            uint8_t* a_lo = a_hi + C::A_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                    // 512 items, 4 per converter thread, in place
+                const int item = rt + j * HALF;
+                const uint32_t off = (uint32_t)(item & 3) * C::A_LBO + (uint32_t)(item >> 2) * 16u;
+                uint4* ph = reinterpret_cast<uint4*>(a_hi + off);
+                uint4* pl = reinterpret_cast<uint4*>(a_lo + off);
+                const float4 v0 = *reinterpret_cast<const float4*>(ph);
+                const float4 v1 = *reinterpret_cast<const float4*>(pl);
+                const float x[8] = {v0.x * a_scale, v0.y * a_scale, v0.z * a_scale, v0.w * a_scale,
+                                    v1.x * a_scale, v1.y * a_scale, v1.z * a_scale, v1.w * a_scale};
+                uint4 hi, lo;
+                tc::split8(x, hi, lo);
+                *ph = hi;
+                *pl = lo;
+            }
+            tc::fence_async_smem();
+            tc::tc_fence_before();
+            named_bar_sync(1, HALF);                          // all 128 converters
+            tc::tc_fence_after();
+            if (rt == 0) {
+                constexpr uint32_t idesc = tc::idesc_f16(GT_ROWS, BN);
+                constexpr uint32_t A_LBO = C::A_LBO, B_LBO = BN * 16;
+                const uint32_t ah0 = tc::smem_u32(a_hi);
+                const uint32_t al0 = ah0 + C::A_BYTES;
+                const uint32_t bh0 = al0 + C::A_BYTES;
+                const uint32_t bl0 = bh0 + C::B_BYTES;
+                const uint32_t acc = tmem + (uint32_t)((chunk & 1) * BN);
+                const bool first = (s % GT_FLUSH) == 0;
+#pragma unroll
+                for (int ks = 0; ks < GT_KS / 16; ++ks) {
+                    const uint64_t ah = tc::smem_desc(ah0 + ks * 2 * A_LBO, A_LBO, 128);
+                    const uint64_t al = tc::smem_desc(al0 + ks * 2 * A_LBO, A_LBO, 128);
+                    const uint64_t bh = tc::smem_desc(bh0 + ks * 2 * B_LBO, B_LBO, 128);
+                    const uint64_t bl = tc::smem_desc(bl0 + ks * 2 * B_LBO, B_LBO, 128);
+                    tc::umma_f16(acc, ah, bh, idesc, !(first && ks == 0));
+                    tc::umma_f16(acc, ah, bl, idesc, 1);
+                    tc::umma_f16(acc, al, bh, idesc, 1);
+                }
+                tc::umma_commit(&empty_bar[stage]);
+                if ((s % GT_FLUSH) == GT_FLUSH - 1 || s == nsl - 1) tc::umma_commit(&chunk_bar[chunk & 1]);
+            }
+            if (pending_chunk >= 0) {     // the chunk that ended one slice ago has drained by now
+                tc::mbar_wait(&chunk_bar[pending_chunk & 1], ph_chunk[pending_chunk & 1]);
+                ph_chunk[pending_chunk & 1] ^= 1;
+                tc::tc_fence_after();
+                flush(pending_chunk & 1);
+                pending_chunk = -1;
+            }
+            if ((s % GT_FLUSH) == GT_FLUSH - 1 && s != nsl - 1) pending_chunk = chunk;
+        }
+        tc::mbar_wait(&chunk_bar[last_chunk & 1], ph_chunk[last_chunk & 1]);
+        tc::tc_fence_after();
+    }
+
+    // ---- epilogue: converter thread = output row; 16 columns at a time
+    if (!is_loader) {
+    const int row = rt;
     const int64_t n = row0 + row;
 #pragma unroll
-    for (int q = 0; q < BN / 32; ++q) {
-        const int c0 = half * 16 + 32 * q;
+    for (int q = 0; q < BN / 16; ++q) {
+        const int c0 = 16 * q;
         float v[16];
         tc::tmem_ld16(tmem_lane + (last_chunk & 1) * BN + c0, v);   // warp-collective: every lane takes part
         const int cbase = col0 + c0;
@@ -442,6 +484,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                 }
             }
         }
+    }
     }
     tc::tc_fence_before();
     __syncthreads();
