@@ -233,6 +233,10 @@ O3DML_API int o3dml_kpconv_gather(const float* query_points, int64_t num_queries
 O3DML_API int o3dml_tc_gemm_test(const float* a, const float* b, float* d, int n, int k, int terms,
                                  void* stream);
 
+/* tcgen05 issue-rate probe (profiling aid): reps x 6 MMAs of M=128 x N x K=16; out[0] = total cycles,
+ * out[1] = cycles spent issuing. */
+O3DML_API int o3dml_tc_mma_rate(int n, int reps, long long* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

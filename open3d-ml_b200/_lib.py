@@ -51,6 +51,7 @@ _SIGNATURES = {
     "o3dml_gather_max": (I, [P, L, I, I, P, I, L, I, L, L, I, P, I, P]),
     "o3dml_kpconv_gather": (I, [P, L, P, L, P, I, I, P, I, P, I, F, P, P]),
     "o3dml_tc_gemm_test": (I, [P, P, P, I, I, I, P]),
+    "o3dml_tc_mma_rate": (I, [I, I, P, P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -15,7 +15,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libo3dml_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-DEBUG = ["-DO3DML_DEBUG_NAN"] if os.environ.get("O3DML_DEBUG_NAN") else []
+DEBUG = (["-DO3DML_DEBUG_NAN"] if os.environ.get("O3DML_DEBUG_NAN") else []) + \
+        (["-DO3DML_DEBUG_TIMING"] if os.environ.get("O3DML_DEBUG_TIMING") else [])
 FLAGS = DEBUG + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr",
          "-ccbin", "/usr/bin/g++"]

@@ -19,7 +19,13 @@
 
 namespace o3dml {
 
-constexpr int GT_THREADS = 256;
+#ifdef O3DML_DEBUG_TIMING
+__device__ long long g_gt_dbg[8192];
+#endif
+
+constexpr int GT_THREADS = 416;   // warp 0 MMA, warps 1-4 loaders, warps 5-8 / 9-12 converter groups
+constexpr int GT_LOADERS = 128;
+constexpr int GT_CONV = 128;
 constexpr int GT_ROWS = 128;
 constexpr int GT_KS = 32;       // channels per k-slice
 constexpr int GT_CH = GT_KS / 8;
@@ -87,6 +93,21 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
+// 1-D bulk async copy (TMA engine) global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tc::smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -100,20 +121,34 @@ struct GtCfg {
     static constexpr int B_BYTES = GT_CH * BN * 16;
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int B_U4 = 2 * GT_CH * BN;                     // uint4 of B per slice (hi + lo)
-    static constexpr int B_PER_THREAD = (B_U4 + GT_THREADS - 1) / GT_THREADS;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;     // two accumulator buffers
-    static constexpr size_t SMEM = (size_t)GT_STAGES * STAGE + GT_MAX_SRC * GT_ROWS * 8 + GT_ROWS * 12 + 256;
+    static constexpr size_t SMEM = (size_t)GT_STAGES * STAGE + GT_MAX_SRC * GT_ROWS * 8 + GT_ROWS * 12 + 512;
 };
 
-// Pipeline (per CTA, one [128 x BN] output tile, k-slices of 32 channels through a GT_STAGES ring):
-//   cp.async   raw fp32 A pieces are parked IN the slots where their fp16 hi / lo words will live
-//              (floats 0-3 of a (row, 8-channel chunk) in the hi slot, floats 4-7 in the lo slot), the
-//              weight image slices go straight to their final place; GT_STAGES-1 slices are in flight
-//   convert    each thread rewrites its own two 16-byte slots in place: x*2^e -> (hi, lo) halves
-//   MMA        one thread issues 3 x 2 tcgen05.mma per slice; its commit frees the stage
-//   flush      every GT_FLUSH slices the TMEM accumulator is added (RN) into registers and the next
-//              chunk starts a fresh accumulator in the other TMEM buffer: the tensor core adds with
-//              truncation (measured -3e-8 relative per accumulation, -5e-5 at K = 7680 otherwise)
+// Pipeline (per CTA, one [128 x BN] output tile, k-slices of 32 channels through a GT_STAGES ring),
+// 12 warps with fixed roles -- the roles are kept in different threads on purpose: the proxy fence that
+// publishes converted operands drains the issuing thread's outstanding memory operations, so a thread
+// that prefetches AND fences never has a load in flight (measured 2.5 us per slice at any depth), and a
+// thread that converts AND issues MMAs serialises 700 + 740 cycles per slice:
+//   warp 0        MMA issuer: waits conv[stage], one elected lane issues 6 tcgen05.mma (descriptors stay
+//                 in uniform registers), tcgen05.commit -> empty[stage] (+ chunk[] at chunk ends)
+//   warps 1-4     loaders: cp.async raw fp32 A pieces straight INTO the slots where their fp16 hi / lo
+//                 words will live + the weight-image slices; cp.async.mbarrier.arrive -> full[stage]
+//   warps 5-8 /   two converter groups taking alternate slices: each thread rewrites its own 16-byte
+//   warps 9-12    slots in place (x * 2^e -> hi, lo), fences, arrives on conv[stage]; group g also owns
+//                 column half g of the accumulator for the flushes and the epilogue
+//   flush         every GT_FLUSH slices the TMEM accumulator is added (RN) into registers and the next
+//                 chunk starts fresh in the other TMEM buffer: the tensor core accumulates with
+//                 truncation (measured -3e-8 relative per accumulation, -5e-5 at K = 7680 otherwise)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
@@ -122,13 +157,22 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     uint8_t* stages = smem;
     const float** rowptr = reinterpret_cast<const float**>(stages + GT_STAGES * C::STAGE);  // [src][row]
     int* rowinfo = reinterpret_cast<int*>(rowptr + GT_MAX_SRC * GT_ROWS);                   // [row][3]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(rowinfo + GT_ROWS * 3);   // full[S], empty[S], chunk[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2 * GT_STAGES + 2);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(rowinfo + GT_ROWS * 3);
+    uint64_t* full_bar = mbar;                       // [S] loaders' cp.async landed
+    uint64_t* conv_bar = mbar + GT_STAGES;           // [S] operands converted + fenced
+    uint64_t* empty_bar = mbar + 2 * GT_STAGES;      // [S] MMAs that read the stage are done
+    uint64_t* chunk_bar = mbar + 3 * GT_STAGES;      // [2] accumulation chunk complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 3 * GT_STAGES + 2);
     __shared__ unsigned amax_warp[GT_THREADS / 32];
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     const int64_t row0 = (int64_t)blockIdx.x * GT_ROWS;
     const int col0 = blockIdx.y * BN;
+#ifdef O3DML_DEBUG_TIMING
+    const bool dbg = blockIdx.x == 0 && blockIdx.y == 0;
+    if (dbg && tid == 0) g_gt_dbg[4000] = clock64();
+#endif
 
     // ---- per-row gather bookkeeping
     if (p.mode == 0) {
@@ -154,9 +198,13 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     }
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < GT_STAGES; ++i) tc::mbar_init(&mbar[i], GT_THREADS / 2);        // full: loaders
-#pragma unroll
-        for (int i = GT_STAGES; i < 2 * GT_STAGES + 2; ++i) tc::mbar_init(&mbar[i], 1);       // empty, chunk
+        for (int i = 0; i < GT_STAGES; ++i) {
+            tc::mbar_init(&full_bar[i], GT_LOADERS + 1);   // loaders + the weight-slice issuer
+            tc::mbar_init(&conv_bar[i], GT_CONV);
+            tc::mbar_init(&empty_bar[i], 1);
+        }
+        tc::mbar_init(&chunk_bar[0], 1);
+        tc::mbar_init(&chunk_bar[1], 1);
         tc::fence_mbar_init();
     }
     __syncthreads();
@@ -168,41 +216,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 
     const int nsl = p.Kpad / GT_KS;
     const size_t img_u4 = (size_t)(p.Kpad / 8) * p.Npad;  // uint4 per image
-
-    // ---- per-thread gather state.  The two (row, 8-channel chunk) items of a thread are the same in
-    // every slice, so everything that does not depend on the slice index is resolved here once.
-    int it_m[2], it_c[2];
-    const float* it_base[2];      // conv: pixel (iy0, ix0) of the row, rows mode with one source: the row
-    unsigned it_taps[2];          // conv: bit t set when tap t lies inside the image
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const int item = tid + it * GT_THREADS;
-        it_m[it] = item >> 2;          // 4 consecutive lanes read the 4 x 32 B of one row's 128-byte slice:
-        it_c[it] = item & 3;           // 8 cache lines per warp request instead of 32
-        it_base[it] = nullptr;
-        it_taps[it] = 0;
-        const int m = it_m[it];
-        if (p.mode == 1) {
-            if (rowinfo[m * 3] >= 0) {
-                const int iy0 = rowinfo[m * 3 + 1], ix0 = rowinfo[m * 3 + 2];
-                it_base[it] = p.src[0].data + ((int64_t)rowinfo[m * 3] + (int64_t)iy0 * p.W + ix0) * p.C;
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int iy = iy0 + t / 3, ix = ix0 + t % 3;
-                    if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) it_taps[it] |= 1u << t;
-                }
-            }
-        } else if (p.nsrc == 1) {
-            it_base[it] = rowptr[m];
-        }
-    }
     const bool conv_fast = p.mode == 1 && (p.C % GT_KS) == 0;   // a 32-channel slice never straddles taps
     const int slices_per_tap = conv_fast ? p.C / GT_KS : 1;
-    auto a_src = [&](int s, int it) -> const float* {
-        const int m = it_m[it], c = it_c[it];
+
+    // source address of the 8 floats of (row m, chunk c) in slice s; nullptr = zeros
+    auto a_src = [&](int s, int m, int c) -> const float* {
         const int k = s * GT_KS + c * 8;
         if (k >= p.K) return nullptr;
         if (p.mode == 1) {
+            if (rowinfo[m * 3] < 0) return nullptr;
             int tap, cc;
             if (conv_fast) {
                 tap = s / slices_per_tap;
@@ -211,10 +233,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                 tap = k / p.C;
                 cc = k - tap * p.C;
             }
-            if (!((it_taps[it] >> tap) & 1u)) return nullptr;
-            return it_base[it] + ((int64_t)(tap / 3) * p.W + (tap % 3)) * p.C + cc;
+            const int iy = rowinfo[m * 3 + 1] + tap / 3, ix = rowinfo[m * 3 + 2] + tap % 3;
+            if (iy < 0 || iy >= p.H || ix < 0 || ix >= p.W) return nullptr;
+            return p.src[0].data + ((int64_t)rowinfo[m * 3] + (int64_t)iy * p.W + ix) * p.C + cc;
         }
-        if (p.nsrc == 1) return it_base[it] ? it_base[it] + k : nullptr;
         int sidx = 0;
         while (sidx + 1 < p.nsrc && k >= p.koff[sidx + 1]) ++sidx;
         const float* base = rowptr[sidx * GT_ROWS + m];
@@ -222,26 +244,57 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     };
 
     float a_scale, out_scale;
-    {   // ---- range pass: max |A| over this CTA's tile -> exact power-of-two scale
-        float mx4[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int s0 = 0; s0 < nsl; s0 += 4) {
+    {   // ---- range pass: max |A| over this CTA's tile -> exact power-of-two scale (all threads)
+        float mx = 0.f;
+        if (p.mode == 1) {
+            // conv: every tap of every row lies in ONE contiguous pixel span of the NHWC input (a superset
+            // is fine for an upper bound) -> a single coalesced sweep instead of 9 gathers per row
+            const int64_t per = (int64_t)p.OH * p.OW;
+            const int64_t n_last = min(row0 + GT_ROWS, p.N) - 1;
+            auto in_pix = [&](int64_t n, int dy, int dx) {
+                const int64_t b = n / per, r = n % per;
+                const int64_t iy = (r / p.OW) * p.stride - 1 + dy, ix = (r % p.OW) * p.stride - 1 + dx;
+                return b * p.H * p.W + iy * p.W + ix;
+            };
+            const int64_t tot_pix = (p.N / per) * (int64_t)p.H * p.W;
+            int64_t lo = max((int64_t)0, in_pix(row0, 0, 0));
+            int64_t hi = min(tot_pix - 1, in_pix(n_last, 2, 2));
+            const float4* base = reinterpret_cast<const float4*>(p.src[0].data + lo * p.C);
+            const int64_t n4 = (hi - lo + 1) * p.C / 4;
+            for (int64_t i = tid; i < n4; i += 4 * GT_THREADS) {
+                float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {       // four slices in flight: independent loads and maxima
+                for (int u = 0; u < 4; ++u)
+                    v[u] = (i + u * GT_THREADS < n4) ? base[i + u * GT_THREADS] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int it = 0; it < 2; ++it) {
-                    const float* src = (s0 + u < nsl) ? a_src(s0 + u, it) : nullptr;
-                    if (src) {
-                        const float4 v0 = *reinterpret_cast<const float4*>(src);
-                        const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
-                        mx4[u] = fmaxf(mx4[u], fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))));
-                        mx4[u] = fmaxf(mx4[u], fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w))));
+                for (int u = 0; u < 4; ++u)
+                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
+            }
+        } else {
+            const int total = nsl * (GT_ROWS * GT_CH);            // (slice, row, chunk) items
+            for (int i0 = tid; i0 < total; i0 += 4 * GT_THREADS) {
+                float4 v[4][2];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {                      // 4 independent gathers in flight per thread
+                    const int i = i0 + u * GT_THREADS;
+                    const float* src = nullptr;
+                    if (i < total) {
+                        const int s = i / (GT_ROWS * GT_CH), rem = i - s * (GT_ROWS * GT_CH);
+                        src = a_src(s, rem >> 2, rem & 3);
                     }
+                    v[u][0] = src ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[u][1] = src ? *reinterpret_cast<const float4*>(src + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u][h].x), fabsf(v[u][h].y)),
+                                             fmaxf(fabsf(v[u][h].z), fabsf(v[u][h].w))));
             }
         }
-        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         const unsigned wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));  // mx >= 0: bits are ordered
-        if ((tid & 31) == 0) amax_warp[warp] = wmx;
+        if ((tid & 31) == 0) amax_warp[tid >> 5] = wmx;
         __syncthreads();
         unsigned bm = 0;
 #pragma unroll
@@ -253,34 +306,89 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         a_scale = ldexpf(1.f, e);
         out_scale = ldexpf(1.f, -e - p.wexp);
     }
-
-    // ---- warp-specialised pipeline.  Warps 0-3 only LOAD (cp.async, completion signalled through
-    // full[stage] by cp.async.mbarrier.arrive); warps 4-7 CONVERT in place, fence, and one of their
-    // threads issues the MMAs whose commit frees the stage (empty[stage]).  Keeping the two roles in
-    // different threads matters: fence.proxy.async drains the issuing thread's outstanding cp.async,
-    // so a thread that both prefetches and fences never has a load in flight across the fence
-    // (measured: 2.5 us per k-slice regardless of the prefetch depth).
-    uint64_t* full_bar = mbar;                       // [GT_STAGES], 128 loader arrivals
-    uint64_t* empty_bar = mbar + GT_STAGES;          // [GT_STAGES], tcgen05.commit
-    uint64_t* chunk_bar = mbar + 2 * GT_STAGES;      // [2]
-    constexpr int HALF = GT_THREADS / 2;
-    const bool is_loader = tid < HALF;
-    const int rt = tid & (HALF - 1);                 // thread index inside its role
-    const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float racc[BN];                                  // converters: RN-accumulated chunk sums of their row
-#pragma unroll
-    for (int i = 0; i < BN; ++i) racc[i] = 0.f;
+#ifdef O3DML_DEBUG_TIMING
+    if (dbg && tid == 0) g_gt_dbg[4001] = clock64();
+#endif
     const int last_chunk = (nsl - 1) / GT_FLUSH;
 
-    if (is_loader) {
-        // ------------------------------------------------------------------ loaders
-        int lm[4], lc[4];
-        const float* lbase[4];
-        unsigned ltaps[4];
+    if (warp == 0) {
+        // ================================================================= MMA issuer
+        constexpr uint32_t idesc = tc::idesc_f16(GT_ROWS, BN);
+        constexpr uint32_t A_LBO = C::A_LBO, B_LBO = BN * 16;
+        // this warp also feeds the weight-image slices: 2 x GT_CH contiguous [BN x 16 B] segments per
+        // slice go to the bulk-copy engine (8 copies instead of BN*8 cp.async), counted in bytes on full[]
+        const uint4* b_img0 = p.wimg + col0;
+        const size_t b_step = (size_t)GT_CH * p.Npad;
+        auto issue_b = [&](int sl) {
+            const int st = sl % GT_STAGES;
+            uint4* bdst = reinterpret_cast<uint4*>(stages + (size_t)st * C::STAGE + 2 * C::A_BYTES);
+            mbar_arrive_expect_tx(&full_bar[st], 2 * C::B_BYTES);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                // 512 (row, chunk) items, 4 per loader thread
-            const int item = rt + j * HALF;
-            lm[j] = item >> 2;
+            for (int img = 0; img < 2; ++img)
+#pragma unroll
+                for (int cc = 0; cc < GT_CH; ++cc)
+                    bulk_copy_g2s(bdst + (img * GT_CH + cc) * BN,
+                                  b_img0 + img * img_u4 + (size_t)sl * b_step + (size_t)cc * p.Npad, BN * 16,
+                                  &full_bar[st]);
+        };
+        if (elect_one()) {
+            for (int sl = 0; sl < GT_STAGES && sl < nsl; ++sl) issue_b(sl);
+        }
+        __syncwarp();
+        for (int s = 0; s < nsl; ++s) {
+            const int stage = s % GT_STAGES, use = s / GT_STAGES, chunk = s / GT_FLUSH;
+#ifdef O3DML_DEBUG_TIMING
+            const long long tm0 = clock64();
+#endif
+            tc::mbar_wait(&conv_bar[stage], use & 1);
+            tc::tc_fence_after();
+#ifdef O3DML_DEBUG_TIMING
+            const long long tm1 = clock64();
+#endif
+            if (elect_one()) {
+                const uint32_t ah0 = tc::smem_u32(stages + (size_t)stage * C::STAGE);
+                const uint32_t al0 = ah0 + C::A_BYTES;
+                const uint32_t bh0 = al0 + C::A_BYTES;
+                const uint32_t bl0 = bh0 + C::B_BYTES;
+                const uint32_t acc = tmem + (uint32_t)((chunk & 1) * BN);
+                const bool first = (s % GT_FLUSH) == 0;
+#pragma unroll
+                for (int ks = 0; ks < GT_KS / 16; ++ks) {
+                    const uint64_t ah = tc::smem_desc(ah0 + ks * 2 * A_LBO, A_LBO, 128);
+                    const uint64_t al = tc::smem_desc(al0 + ks * 2 * A_LBO, A_LBO, 128);
+                    const uint64_t bh = tc::smem_desc(bh0 + ks * 2 * B_LBO, B_LBO, 128);
+                    const uint64_t bl = tc::smem_desc(bl0 + ks * 2 * B_LBO, B_LBO, 128);
+                    tc::umma_f16(acc, ah, bh, idesc, !(first && ks == 0));
+                    tc::umma_f16(acc, ah, bl, idesc, 1);
+                    tc::umma_f16(acc, al, bh, idesc, 1);
+                }
+                tc::umma_commit(&empty_bar[stage]);
+                if ((s % GT_FLUSH) == GT_FLUSH - 1 || s == nsl - 1) tc::umma_commit(&chunk_bar[chunk & 1]);
+#ifdef O3DML_DEBUG_TIMING
+                if (dbg && s < 300) { g_gt_dbg[2000 + 3 * s] = tm0; g_gt_dbg[2001 + 3 * s] = tm1; g_gt_dbg[2002 + 3 * s] = clock64(); }
+#endif
+            }
+            __syncwarp();
+            // refill the weight half of the stage that slice s-1 used (its MMAs were issued one slice ago)
+            const int sn = s + GT_STAGES - 1;
+            if (s >= 1 && sn < nsl) {
+                tc::mbar_wait(&empty_bar[(s - 1) % GT_STAGES], ((s - 1) / GT_STAGES) & 1);
+                if (elect_one()) issue_b(sn);
+                __syncwarp();
+            }
+        }
+    } else if (warp < 5) {
+        // ================================================================= loaders (128 threads)
+        const int rt = tid - 32;
+        constexpr int LA = (GT_ROWS * GT_CH) / GT_LOADERS;                    // (row, chunk) items per thread
+        // everything that does not depend on the slice index is resolved once
+        int lm[LA], lc[LA];
+        const float* lbase[LA];      // conv: pixel (iy0, ix0) of the row; rows mode with one source: the row
+        unsigned ltaps[LA];          // conv: bit t set when tap t lies inside the image
+#pragma unroll
+        for (int j = 0; j < LA; ++j) {
+            const int item = rt + j * GT_LOADERS;
+            lm[j] = item >> 2;       // 4 consecutive lanes read the 4 x 32 B of one row's 128-byte slice
             lc[j] = item & 3;
             lbase[j] = nullptr;
             ltaps[j] = 0;
@@ -299,85 +407,133 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                 lbase[j] = rowptr[m];
             }
         }
-        constexpr int LB = (C::B_U4 + HALF - 1) / HALF;   // weight-image words per loader thread
-        const uint4* b_src[LB];
+        // the weight-image slice is 2 x GT_CH contiguous [BN x 16 B] segments: one loader thread hands them
+        // to the bulk-copy engine (8 copies of BN*16 bytes instead of BN*8 cp.async instructions)
+        // A pieces travel global -> registers -> shared (LDG.128 / STS.128): cp.async issued from here ran
+        // at ~30 cycles per warp instruction (1000 cycles per slice).  Two slices stay in flight in
+        // registers; these threads never execute a proxy fence, so nothing drains the loads early.
+        // a single warp retires ~1 dependent instruction per 4-6 cycles, so the per-slice work of a loader
+        // thread has to stay well under 100 instructions: slices are visited in order and the source
+        // address of every piece is advanced incrementally (no division in the loop)
+        int ld_tap = 0, ld_in_tap = 0, ld_sl = 0;     // state of the NEXT slice to load (conv_fast)
+        int64_t ld_toff = 0;                          // float offset of the current tap + channel block
+        constexpr int LOOK = 2;
+        float4 rg[LOOK + 1][LA][2];
+        auto load_slice = [&](int slot) {             // loads slice ld_sl into register slot `slot`
+            const int sl = ld_sl;
 #pragma unroll
-        for (int j = 0; j < LB; ++j) {
-            const int idx = rt + j * HALF;
-            const int img = idx / (GT_CH * BN), rem = idx % (GT_CH * BN);
-            b_src[j] = p.wimg + img * img_u4 + (size_t)(rem / BN) * p.Npad + col0 + (rem % BN);
-        }
-        const size_t b_step = (size_t)GT_CH * p.Npad;
-        for (int s = 0; s < nsl; ++s) {
-            const int stage = s % GT_STAGES, use = s / GT_STAGES;
-            if (use >= 1) tc::mbar_wait(&empty_bar[stage], (use - 1) & 1);   // MMAs of slice s-STAGES done
-            uint8_t* a_hi = stages + (size_t)stage * C::STAGE;
-            uint8_t* a_lo = a_hi + C::A_BYTES;
-            uint4* bdst = reinterpret_cast<uint4*>(a_lo + C::A_BYTES);
-            int tap = 0, cc0 = s * GT_KS;
-            if (p.mode == 1) {
-                if (conv_fast) {
-                    tap = s / slices_per_tap;
-                    cc0 = (s - tap * slices_per_tap) * GT_KS;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = s * GT_KS + lc[j] * 8;
+            for (int j = 0; j < LA; ++j) {
                 const float* src = nullptr;
-                if (k < p.K) {
-                    if (p.mode == 1) {
-                        int t = tap, cc = cc0 + lc[j] * 8;
-                        if (!conv_fast) {
-                            t = k / p.C;
-                            cc = k - t * p.C;
+                if (sl < nsl) {
+                    const int k = sl * GT_KS + lc[j] * 8;
+                    if (k < p.K) {
+                        if (conv_fast) {
+                            if ((ltaps[j] >> ld_tap) & 1u) src = lbase[j] + ld_toff + lc[j] * 8;
+                        } else if (p.mode == 1) {
+                            const int t = k / p.C, cc = k - t * p.C;
+                            if ((ltaps[j] >> t) & 1u) src = lbase[j] + ((int64_t)(t / 3) * p.W + (t % 3)) * p.C + cc;
+                        } else if (p.nsrc == 1) {
+                            if (lbase[j]) src = lbase[j] + k;
+                        } else {
+                            src = a_src(sl, lm[j], lc[j]);
                         }
-                        if ((ltaps[j] >> t) & 1u) src = lbase[j] + ((int64_t)(t / 3) * p.W + (t % 3)) * p.C + cc;
-                    } else if (p.nsrc == 1) {
-                        if (lbase[j]) src = lbase[j] + k;
-                    } else {
-                        int sidx = 0;
-                        while (sidx + 1 < p.nsrc && k >= p.koff[sidx + 1]) ++sidx;
-                        const float* base = rowptr[sidx * GT_ROWS + lm[j]];
-                        if (base) src = base + (k - p.koff[sidx]);
                     }
                 }
-                const void* g0 = src ? (const void*)src : (const void*)p.wimg;
-                const void* g1 = src ? (const void*)(src + 4) : (const void*)p.wimg;
-                const uint32_t off = (uint32_t)lc[j] * C::A_LBO + (uint32_t)lm[j] * 16u;
-                cp_async16(a_hi + off, g0, src ? 16 : 0);
-                cp_async16(a_lo + off, g1, src ? 16 : 0);
+                rg[slot][j][0] = src ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                rg[slot][j][1] = src ? *reinterpret_cast<const float4*>(src + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-#pragma unroll
-            for (int j = 0; j < LB; ++j) {
-                const int idx = rt + j * HALF;
-                if (idx < C::B_U4) cp_async16(&bdst[idx], b_src[j] + (size_t)s * b_step, 16);
-            }
-            cp_async_arrive(&full_bar[stage]);
-        }
-        cp_async_wait<0>();
-    } else {
-        // ---------------------------------------------------------------- converters + MMA + flush
-        auto flush = [&](int buf) {       // racc += TMEM accumulator buffer `buf` (round to nearest)
-#pragma unroll
-            for (int q = 0; q < BN / 16; ++q) {
-                float v[16];
-                tc::tmem_ld16(tmem_lane + buf * BN + q * 16, v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) racc[q * 16 + j] += v[j];
+            ++ld_sl;
+            if (conv_fast) {
+                ld_toff += GT_KS;
+                if (++ld_in_tap == slices_per_tap) {
+                    ld_in_tap = 0;
+                    ++ld_tap;
+                    ld_toff = ((int64_t)(ld_tap / 3) * p.W + (ld_tap % 3)) * p.C;
+                }
             }
         };
+#pragma unroll
+        for (int l = 0; l < LOOK; ++l) load_slice(l);
+        for (int s0 = 0; s0 < nsl; s0 += LOOK + 1) {
+#pragma unroll
+            for (int u = 0; u < LOOK + 1; ++u) {       // register slots are compile-time indices
+                const int s = s0 + u;
+                if (s < nsl) {
+                    load_slice((u + LOOK) % (LOOK + 1));
+                    const int stage = s % GT_STAGES, use = s / GT_STAGES;
+#ifdef O3DML_DEBUG_TIMING
+                    const long long tl0 = clock64();
+#endif
+                    if (use >= 1) tc::mbar_wait(&empty_bar[stage], (use - 1) & 1);   // MMAs of slice s-STAGES done
+#ifdef O3DML_DEBUG_TIMING
+                    const long long tl1 = clock64();
+#endif
+                    uint8_t* a_hi = stages + (size_t)stage * C::STAGE;
+                    uint8_t* a_lo = a_hi + C::A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < LA; ++j) {
+                        const uint32_t off = (uint32_t)lc[j] * C::A_LBO + (uint32_t)lm[j] * 16u;
+                        *reinterpret_cast<float4*>(a_hi + off) = rg[u][j][0];
+                        *reinterpret_cast<float4*>(a_lo + off) = rg[u][j][1];
+                    }
+#ifdef O3DML_DEBUG_TIMING
+                    const long long tl2 = clock64();
+#endif
+                    mbar_arrive(&full_bar[stage]);                                   // release: stores visible
+#ifdef O3DML_DEBUG_TIMING
+                    if (dbg && rt == 0 && s < 700) {
+                        g_gt_dbg[1000 + 4 * s] = tl0; g_gt_dbg[1001 + 4 * s] = tl1; g_gt_dbg[1002 + 4 * s] = tl2;
+                        g_gt_dbg[1003 + 4 * s] = clock64();
+                    }
+#endif
+                }
+            }
+        }
+    } else {
+        // ================================================================= converters + flush + epilogue
+        const int grp = (warp - 5) >> 2;               // converter group = column half
+        const int rt = (warp & 3) * 32 + (tid & 31);   // output row = TMEM lane this thread can read
+        const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        constexpr int HB = BN / 2 < 16 ? 16 : BN / 2;  // columns owned by a group
+        constexpr int NQ = HB / 16;
+        float racc[HB];
+#pragma unroll
+        for (int i = 0; i < HB; ++i) racc[i] = 0.f;
+        const bool owns_cols = (BN >= 32) || grp == 0;
+        const int colbase = (BN >= 32) ? grp * HB : 0;
         uint32_t ph_chunk[2] = {0, 0};
-        int pending_chunk = -1;
-        for (int s = 0; s < nsl; ++s) {
+        int next_flush = 0;                            // first chunk this group has not folded yet
+        auto fold = [&](int chunk) {                   // racc += accumulator of `chunk` (RN adds)
+            tc::mbar_wait(&chunk_bar[chunk & 1], ph_chunk[chunk & 1]);
+            ph_chunk[chunk & 1] ^= 1;
+            tc::tc_fence_after();
+            if (owns_cols) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    float v[16];
+                    tc::tmem_ld16(tmem_lane + (chunk & 1) * BN + colbase + q * 16, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) racc[q * 16 + j] += v[j];
+                }
+            }
+            tc::tc_fence_before();
+        };
+        for (int s = grp; s < nsl; s += 2) {
             const int stage = s % GT_STAGES, use = s / GT_STAGES;
-            const int chunk = s / GT_FLUSH;
-            tc::mbar_wait(&full_bar[stage], use & 1);        // every piece of slice s has landed
+            // chunks that ended at least one slice ago have drained: fold them before converting on
+            while (next_flush < last_chunk && s >= (next_flush + 1) * GT_FLUSH + 1) fold(next_flush++);
+#ifdef O3DML_DEBUG_TIMING
+            const long long tq0 = clock64();
+#endif
+            tc::mbar_wait(&full_bar[stage], use & 1);         // every piece of slice s has landed
+#ifdef O3DML_DEBUG_TIMING
+            const long long tq1 = clock64();
+#endif
             uint8_t* a_hi = stages + (size_t)stage * C::STAGE;
             uint8_t* a_lo = a_hi + C::A_BYTES;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {                    // 512 items, 4 per converter thread, in place
-                const int item = rt + j * HALF;
+            for (int j = 0; j < (GT_ROWS * GT_CH) / GT_CONV; ++j) {   // 512 items, 4 per thread, in place
+                const int item = rt + j * GT_CONV;
                 const uint32_t off = (uint32_t)(item & 3) * C::A_LBO + (uint32_t)(item >> 2) * 16u;
                 uint4* ph = reinterpret_cast<uint4*>(a_hi + off);
                 uint4* pl = reinterpret_cast<uint4*>(a_lo + off);
@@ -391,103 +547,83 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                 *pl = lo;
             }
             tc::fence_async_smem();
-            tc::tc_fence_before();
-            named_bar_sync(1, HALF);                          // all 128 converters
-            tc::tc_fence_after();
-            if (rt == 0) {
-                constexpr uint32_t idesc = tc::idesc_f16(GT_ROWS, BN);
-                constexpr uint32_t A_LBO = C::A_LBO, B_LBO = BN * 16;
-                const uint32_t ah0 = tc::smem_u32(a_hi);
-                const uint32_t al0 = ah0 + C::A_BYTES;
-                const uint32_t bh0 = al0 + C::A_BYTES;
-                const uint32_t bl0 = bh0 + C::B_BYTES;
-                const uint32_t acc = tmem + (uint32_t)((chunk & 1) * BN);
-                const bool first = (s % GT_FLUSH) == 0;
-#pragma unroll
-                for (int ks = 0; ks < GT_KS / 16; ++ks) {
-                    const uint64_t ah = tc::smem_desc(ah0 + ks * 2 * A_LBO, A_LBO, 128);
-                    const uint64_t al = tc::smem_desc(al0 + ks * 2 * A_LBO, A_LBO, 128);
-                    const uint64_t bh = tc::smem_desc(bh0 + ks * 2 * B_LBO, B_LBO, 128);
-                    const uint64_t bl = tc::smem_desc(bl0 + ks * 2 * B_LBO, B_LBO, 128);
-                    tc::umma_f16(acc, ah, bh, idesc, !(first && ks == 0));
-                    tc::umma_f16(acc, ah, bl, idesc, 1);
-                    tc::umma_f16(acc, al, bh, idesc, 1);
-                }
-                tc::umma_commit(&empty_bar[stage]);
-                if ((s % GT_FLUSH) == GT_FLUSH - 1 || s == nsl - 1) tc::umma_commit(&chunk_bar[chunk & 1]);
+            mbar_arrive(&conv_bar[stage]);
+#ifdef O3DML_DEBUG_TIMING
+            if (dbg && rt == 0 && s < 900) {
+                g_gt_dbg[4 * s + 0] = tq0; g_gt_dbg[4 * s + 1] = tq1; g_gt_dbg[4 * s + 2] = clock64();
             }
-            if (pending_chunk >= 0) {     // the chunk that ended one slice ago has drained by now
-                tc::mbar_wait(&chunk_bar[pending_chunk & 1], ph_chunk[pending_chunk & 1]);
-                ph_chunk[pending_chunk & 1] ^= 1;
-                tc::tc_fence_after();
-                flush(pending_chunk & 1);
-                pending_chunk = -1;
-            }
-            if ((s % GT_FLUSH) == GT_FLUSH - 1 && s != nsl - 1) pending_chunk = chunk;
+#endif
         }
+        while (next_flush < last_chunk) fold(next_flush++);
         tc::mbar_wait(&chunk_bar[last_chunk & 1], ph_chunk[last_chunk & 1]);
         tc::tc_fence_after();
-    }
-
-    // ---- epilogue: converter thread = output row; 16 columns at a time
-    if (!is_loader) {
-    const int row = rt;
-    const int64_t n = row0 + row;
+#ifdef O3DML_DEBUG_TIMING
+        if (dbg && rt == 0 && grp == 0) g_gt_dbg[4002] = clock64();
+#endif
+        // ---- epilogue: thread = output row, this group's column half, 16 columns at a time
+        const int64_t n = row0 + rt;
+        if (owns_cols) {
 #pragma unroll
-    for (int q = 0; q < BN / 16; ++q) {
-        const int c0 = 16 * q;
-        float v[16];
-        tc::tmem_ld16(tmem_lane + (last_chunk & 1) * BN + c0, v);   // warp-collective: every lane takes part
-        const int cbase = col0 + c0;
-        if (n >= p.N || cbase >= p.Cout) continue;
+            for (int q = 0; q < NQ; ++q) {
+                const int c0 = colbase + 16 * q;
+                float v[16];
+                tc::tmem_ld16(tmem_lane + (last_chunk & 1) * BN + c0, v);   // warp-collective
+                const int cbase = col0 + c0;
+                if (n >= p.N || cbase >= p.Cout) continue;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int c = cbase + j;
-            if (c < p.Cout) {
-                float x = (v[j] + racc[q * 16 + j]) * out_scale;   // exact: undoes the power-of-two scalings
-                x = fmaf(x, p.scale ? p.scale[c] : 1.f, p.shift ? p.shift[c] : 0.f);
-                if (p.residual) x += p.residual[(size_t)n * p.res_ld + c];
-                v[j] = apply_act(x, p.act, p.slope);
-            }
-        }
-        if (p.out_mode == 0) {
-            float* o = p.out + (size_t)n * p.out_ld + cbase;
-            if (cbase + 15 < p.Cout && (p.out_ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) {
+                for (int j = 0; j < 16; ++j) {
+                    const int c = cbase + j;
+                    if (c < p.Cout) {
+                        float x = (v[j] + racc[q * 16 + j]) * out_scale;   // exact: undoes the 2^e scalings
+                        x = fmaf(x, p.scale ? p.scale[c] : 1.f, p.shift ? p.shift[c] : 0.f);
+                        if (p.residual) x += p.residual[(size_t)n * p.res_ld + c];
+                        v[j] = apply_act(x, p.act, p.slope);
+                    }
+                }
+                if (p.out_mode == 0) {
+                    float* o = p.out + (size_t)n * p.out_ld + cbase;
+                    if (cbase + 15 < p.Cout && (p.out_ld & 3) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    *reinterpret_cast<float4*>(o + 4 * u) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-            } else {
+                        for (int u = 0; u < 4; ++u)
+                            *reinterpret_cast<float4*>(o + 4 * u) =
+                                make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (cbase + j < p.Cout) o[j] = v[j];
-            }
-        } else if (p.out_mode == 1) {
-            const int64_t b = n / p.plane, pix = n % p.plane;
+                        for (int j = 0; j < 16; ++j)
+                            if (cbase + j < p.Cout) o[j] = v[j];
+                    }
+                } else if (p.out_mode == 1) {
+                    const int64_t b = n / p.plane, pix = n % p.plane;
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (cbase + j < p.Cout) p.out[((size_t)b * p.Cout + cbase + j) * p.plane + pix] = v[j];
-        } else {
-            const int64_t per = (int64_t)p.dIH * p.dIW;
-            const int64_t b = n / per;
-            const int r = (int)(n % per);
-            const int iy = r / p.dIW, ix = r % p.dIW;
-            const int OWd = p.dIW * p.ds;
+                    for (int j = 0; j < 16; ++j)
+                        if (cbase + j < p.Cout) p.out[((size_t)b * p.Cout + cbase + j) * p.plane + pix] = v[j];
+                } else {
+                    const int64_t per = (int64_t)p.dIH * p.dIW;
+                    const int64_t b = n / per;
+                    const int r = (int)(n % per);
+                    const int iy = r / p.dIW, ix = r % p.dIW;
+                    const int OWd = p.dIW * p.ds;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int c = cbase + j;
-                if (c < p.Cout) {
-                    const int sub = c / p.dC, co = c - sub * p.dC;
-                    const int dy = sub / p.ds, dx = sub - dy * p.ds;
-                    const size_t opix = ((size_t)b * p.dIH * p.ds + (size_t)iy * p.ds + dy) * OWd +
-                                        (size_t)ix * p.ds + dx;
-                    p.out[opix * p.out_ld + co] = v[j];
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = cbase + j;
+                        if (c < p.Cout) {
+                            const int sub = c / p.dC, co = c - sub * p.dC;
+                            const int dy = sub / p.ds, dx = sub - dy * p.ds;
+                            const size_t opix = ((size_t)b * p.dIH * p.ds + (size_t)iy * p.ds + dy) * OWd +
+                                                (size_t)ix * p.ds + dx;
+                            p.out[opix * p.out_ld + co] = v[j];
+                        }
+                    }
                 }
             }
         }
-    }
     }
     tc::tc_fence_before();
     __syncthreads();
+#ifdef O3DML_DEBUG_TIMING
+    if (dbg && tid == 0) g_gt_dbg[4003] = clock64();
+#endif
     if (warp == 0) tc::tmem_dealloc<C::TMEM_COLS>(tmem);
 }
 
@@ -618,3 +754,9 @@ extern "C" int o3dml_deconv_nhwc_tc(const float* in, int batch, int H, int W, in
     p.ds = stride; p.dIH = H; p.dIW = W; p.dC = out_channels;
     return gemm_tc_launch(p, (cudaStream_t)stream);
 }
+
+#ifdef O3DML_DEBUG_TIMING
+extern "C" __attribute__((visibility("default"))) int o3dml_gt_debug_read(long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, o3dml::g_gt_dbg, sizeof(long long) * n);
+}
+#endif

@@ -86,9 +86,65 @@ tc_gemm_test_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
     if (warp == 0) tc::tmem_dealloc<256>(taddr);
 }
 
+
+// Issue-rate probe: `reps` x 6 MMAs (M=128, N, K=16 each) on resident (zeroed) operands, one commit;
+// out[0] = cycles from first issue to completion, out[1] = cycles spent issuing.
+__global__ void __launch_bounds__(128, 1)
+tc_mma_rate_kernel(int N, int reps, long long* out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int a_bytes = 4 * 128 * 16, b_bytes = 4 * N * 16;     // 32 channels each
+    for (int i = tid; i < (2 * a_bytes + 2 * b_bytes) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    tc::fence_async_smem();
+    if (tid == 0) { tc::mbar_init(&mbar, 1); tc::fence_mbar_init(); }
+    __syncthreads();
+    if (warp == 0) tc::tmem_alloc<256>(&tmem_base);
+    tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
+    const uint32_t taddr = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = tc::idesc_f16(128, N);
+        const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)N * 16;
+        const uint32_t ah0 = tc::smem_u32(smem), al0 = ah0 + a_bytes, bh0 = al0 + a_bytes, bl0 = bh0 + b_bytes;
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t ah = tc::smem_desc(ah0 + ks * 2 * a_lbo, a_lbo, 128);
+                const uint64_t al = tc::smem_desc(al0 + ks * 2 * a_lbo, a_lbo, 128);
+                const uint64_t bh = tc::smem_desc(bh0 + ks * 2 * b_lbo, b_lbo, 128);
+                const uint64_t bl = tc::smem_desc(bl0 + ks * 2 * b_lbo, b_lbo, 128);
+                tc::umma_f16(taddr, ah, bh, idesc, 1);
+                tc::umma_f16(taddr, ah, bl, idesc, 1);
+                tc::umma_f16(taddr, al, bh, idesc, 1);
+            }
+        }
+        const long long t1 = clock64();
+        tc::umma_commit(&mbar);
+        tc::mbar_wait(&mbar, 0);
+        const long long t2 = clock64();
+        out[0] = t2 - t0;
+        out[1] = t1 - t0;
+    }
+    __syncthreads();
+    tc::tc_fence_before(); __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(taddr);
+}
+
 }  // namespace o3dml
 
 using namespace o3dml;
+
+extern "C" int o3dml_tc_mma_rate(int n, int reps, long long* out, void* stream) {
+    O3DML_CHECK(n >= 16 && n <= 256 && (n % 16) == 0, "tc_mma_rate: bad N");
+    const size_t smem = 2 * 4 * 128 * 16 + 2 * 4 * (size_t)n * 16;
+    O3DML_CUDA(cudaFuncSetAttribute(tc_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(n, reps, out);
+    O3DML_LAUNCH_CHECK();
+    return O3DML_OK;
+}
+
 
 extern "C" int o3dml_tc_gemm_test(const float* a, const float* b, float* d, int n, int k, int terms,
                                   void* stream) {
