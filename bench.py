@@ -178,6 +178,7 @@ class PointPillarsWorkload:
     name = "PointPillars forward, synthetic KITTI frames (~20 000 pts), BASELINE configs[1]"
     short = "pointpillars_kitti"
     manifest = "pointpillars_kitti.manifest.json"
+    dense_gflop_per_frame = 68.3   # SECOND + SECONDFPN + head at 496 x 432
 
     def __init__(self, frames=1, n=20000):
         self.B, self.N = frames, n
@@ -333,6 +334,18 @@ def run_b200(args, wl):
             b.record()
             timers.append((stage, d, B * N, a, b))
         model._lfa_pool = timed_lfa
+    dense_timers = []
+    if hasattr(model, "backbone_neck_head"):
+        orig_bnh = model.backbone_neck_head
+
+        def timed_bnh(canvas):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = orig_bnh(canvas)
+            b.record()
+            dense_timers.append((a, b, canvas.shape[0]))
+            return r
+        model.backbone_neck_head = timed_bnh
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -389,6 +402,20 @@ def run_b200(args, wl):
                                         gbs=round(e[2] / (e[0] * 1e-3) / 1e9, 1),
                                         tflops=round(e[3] / (e[0] * 1e-3) / 1e12, 2))
                                 for k, e in sorted(per.items())})
+    if dense_timers:
+        # PointPillars: the dense BEV backbone + neck + head (SECOND/FPN/Anchor3DHead, 20 implicit-GEMM
+        # launches of gemm_tc_kernel) is the dominant kernel class: tensor-core bound
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak_tf = float(d.get("bf16_tflops", 1590.0))
+        tot_ms = sum(a.elapsed_time(b) for a, b, _ in dense_timers)
+        frames = sum(n for _, _, n in dense_timers)
+        gflop = wl.dense_gflop_per_frame * frames
+        ach = gflop / tot_ms            # GFLOP / ms = TFLOP/s
+        roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05, 3xFP16 split): SECOND + SECONDFPN + head, 20 launches/frame",
+                    achieved=round(ach, 2), peak=peak_tf, unit="TFLOP/s", frac=round(ach / peak_tf, 5), traffic=None,
+                    peak_source=("measured bf16 cuBLAS burst (MEASURED_PEAKS.json)" if d else "fallback (B200_PROFILING.md)"),
+                    share_of_step=round(tot_ms / ms, 4), algorithmic_gflop_per_frame=wl.dense_gflop_per_frame,
+                    note="algorithmic FLOPs (68.3 GFLOP/frame, SURVEY 8d); the 3xFP16 split issues 3x that on the tensor pipe")
     # --- cpu baseline (bounded sample, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu:

@@ -148,13 +148,13 @@ def pack_linear(w_kc):
     return PackedWeight(w_kc)
 
 
-TC_MIN_K = int(os.environ.get("O3DML_GEMM_TC_MIN_K", "64"))
+TC_MIN_K = int(os.environ.get("O3DML_GEMM_TC_MIN_K", "128"))
 
 
 def _tc_ok(srcs):
-    """Tensor-core kernel only where it pays: every source 8-channel aligned, and K >= 64 (below that the
-    per-CTA setup of the tcgen05 pipeline costs more than the whole SIMT tile: 71 vs 42 us measured on
-    the 360k x 32 layers of RandLA-Net)."""
+    """Tensor-core kernel only where it pays: every source 8-channel aligned, and K >= 128 (below that the
+    per-CTA setup of the warp-specialised tcgen05 pipeline, one CTA per SM, costs more than the whole
+    SIMT tile: 188 vs ~40 us measured on the 360k-row K<=96 layers of RandLA-Net)."""
     if not USE_TC_GEMM or sum(s.channels for s in srcs) < TC_MIN_K:
         return False
     return all((s.channels % 8 == 0) and (s.ld % 4 == 0) and (s.data % 16 == 0) for s in srcs)
