@@ -226,6 +226,47 @@ def pick_cpu_threads(wl, sd):
     return best
 
 
+class KPConvWorkload:
+    name = "KPConv (KPFCNN) forward, S3DIS-shaped clouds (65 536 pts, rooms pre-gridded at 4 cm), BASELINE configs[3]"
+    short = "kpconv_s3dis"
+    manifest = "kpconv_s3dis.manifest.json"
+    gflop_per_cloud = 90.3   # SURVEY.md 8d (encoder 54.8 + decoder/head 35.5)
+
+    def __init__(self, clouds=4, n=65536):
+        self.B, self.N = clouds, n
+
+    def points_per_step(self):
+        return self.B * self.N
+
+    def _clouds(self, count, seed0):
+        from open3d_ml_b200 import synth
+        return [synth.room_cloud(self.N, seed0 + b) for b in range(count)]
+
+    def build_inputs_gpu(self, rank):
+        from open3d_ml_b200.kpconv import build_batch
+        b = build_batch(self._clouds(self.B, 1000 * rank), self.cfg)
+        return {k: ([pin(t.cpu()) for t in v] if isinstance(v, list) and v and isinstance(v[0], torch.Tensor)
+                    else (pin(v.cpu()) if isinstance(v, torch.Tensor) else v)) for k, v in b.items()}
+
+    def build_inputs_cpu(self, count):
+        from open3d_ml_b200.kpconv import build_batch
+        if torch.cuda.is_available():
+            b = build_batch(self._clouds(count, 0), self.cfg)
+            return {k: ([t.cpu() for t in v] if isinstance(v, list) and v and isinstance(v[0], torch.Tensor)
+                        else (v.cpu() if isinstance(v, torch.Tensor) else v)) for k, v in b.items()}
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers as H
+        return H.kp_batch_tensors(H.kp_batch(self._clouds(count, 0), self.cfg))
+
+    def make_model(self, sd):
+        import open3d_ml_b200 as M
+        return M.KPFCNNB200(sd, self.cfg)
+
+    def cpu_forward(self, sd, inp):
+        from oracle import models_torch as MT
+        return MT.kpfcnn_forward(sd, inp, self.cfg)
+
+
 def load_weights(wl, seed=1):
     from oracle import weights
     man, extra = weights.load_manifest(os.path.join(ROOT, "tests", "golden", wl.manifest))
@@ -416,6 +457,14 @@ def run_b200(args, wl):
                     peak_source=("measured bf16 cuBLAS burst (MEASURED_PEAKS.json)" if d else "fallback (B200_PROFILING.md)"),
                     share_of_step=round(tot_ms / ms, 4), algorithmic_gflop_per_frame=wl.dense_gflop_per_frame,
                     note="algorithmic FLOPs (68.3 GFLOP/frame, SURVEY 8d); the 3xFP16 split issues 3x that on the tensor pipe")
+    if roof is None and hasattr(wl, "gflop_per_cloud"):
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak_tf = float(d.get("bf16_tflops", 1590.0))
+        ach = wl.gflop_per_cloud * wl.B * args.steps / ms
+        roof = dict(bound="tensor", kernel="whole KPFCNN forward (kpconv_gather + gemm_tc_kernel)", achieved=round(ach, 2),
+                    peak=peak_tf, unit="TFLOP/s", frac=round(ach / peak_tf, 5), traffic=None,
+                    peak_source=("measured bf16 cuBLAS burst (MEASURED_PEAKS.json)" if d else "fallback"),
+                    algorithmic_gflop_per_cloud=wl.gflop_per_cloud)
     # --- cpu baseline (bounded sample, N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -452,13 +501,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="randlanet", choices=["randlanet", "pointpillars"])
+    ap.add_argument("--workload", default="randlanet", choices=["randlanet", "pointpillars", "kpconv"])
     ap.add_argument("--units", type=int, default=0, help="clouds / frames per GPU (0 = config default)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
-    wl = RandLAWorkload(args.units or 8) if args.workload == "randlanet" else PointPillarsWorkload(args.units or 1)
+    wl = (RandLAWorkload(args.units or 8) if args.workload == "randlanet" else
+          PointPillarsWorkload(args.units or 1) if args.workload == "pointpillars" else
+          KPConvWorkload(args.units or 4))
     if args.impl == "reference":
         args.steps = min(args.steps, 50)   # bounded CPU sample: each step is one full-size unit
         run_reference(args, wl)

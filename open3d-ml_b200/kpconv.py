@@ -200,3 +200,45 @@ class KPFCNNB200:
         return self._lin("head_softmax", [L.make_src(x)], x.shape[0], "leaky")
 
     __call__ = forward
+
+
+def build_batch(clouds, cfg, device="cuda"):
+    """The index pyramid of KPConvBatch.segmentation_inputs (ml3d/torch/dataloaders/concat_batcher.py:
+    186-305) for a list of (points [n,3], features [n,F]) numpy clouds: per level the conv / pool /
+    upsample neighbour matrices, built with the CUDA fixed-radius search and padded with the shadow id
+    (kpconv.py:2002-2034).  Grid subsampling (a "next" row) uses the numpy barycentre
+    stand-in of open3d_ml_b200.synth.  Returns a dict of CUDA tensors."""
+    import numpy as np
+    from . import ops, synth
+
+    def neighbors(queries, supports, q_lens, s_lens, radius):
+        qs = torch.tensor(np.concatenate([[0], np.cumsum(q_lens)]), dtype=torch.int64, device=device)
+        ss = torch.tensor(np.concatenate([[0], np.cumsum(s_lens)]), dtype=torch.int64, device=device)
+        r = ops.fixed_radius_search(supports, queries, radius, ss, qs, return_distances=False)
+        rs = r.neighbors_row_splits
+        width = int((rs[1:] - rs[:-1]).max()) if rs.numel() > 1 else 0
+        return ops.ragged_to_dense(r.neighbors_index, rs, width,
+                                   torch.tensor([supports.shape[0]], dtype=torch.int32)).to(torch.int64)
+
+    r = cfg["first_subsampling_dl"] * cfg["conv_radius"]
+    dl = cfg["first_subsampling_dl"]
+    out = dict(features=torch.from_numpy(np.concatenate([c[1] for c in clouds])).to(device),
+               points=[], neighbors=[], pools=[], upsamples=[], lengths=[])
+    cur = [c[0] for c in clouds]
+    for lvl in range(cfg["num_layers"]):
+        P = torch.from_numpy(np.concatenate(cur)).to(device)
+        ln = [len(c) for c in cur]
+        out["points"].append(P)
+        out["lengths"].append(ln)
+        out["neighbors"].append(neighbors(P, P, ln, ln, r))
+        if lvl < cfg["num_layers"] - 1:
+            nxt = [synth.grid_subsample(c, 2 * dl) for c in cur]
+            Q = torch.from_numpy(np.concatenate(nxt)).to(device)
+            lq = [len(c) for c in nxt]
+            out["pools"].append(neighbors(Q, P, lq, ln, r))
+            out["upsamples"].append(neighbors(P, Q, ln, lq, 2 * r))
+            cur, dl, r = nxt, 2 * dl, r * 2
+        else:
+            out["pools"].append(torch.zeros((0, 1), dtype=torch.int64, device=device))
+            out["upsamples"].append(torch.zeros((0, 1), dtype=torch.int64, device=device))
+    return out
