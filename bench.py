@@ -61,7 +61,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -398,6 +398,8 @@ def run_b200(args, wl):
     clk = clocks.stop() if rank == 0 else None
     if hasattr(model, "_lfa_pool"):
         model._lfa_pool = orig
+    if hasattr(model, "backbone_neck_head"):
+        model.backbone_neck_head = orig_bnh      # timers cover the resident region only
     # --- e2e
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()

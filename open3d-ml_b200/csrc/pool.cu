@@ -47,10 +47,11 @@ gather_max_kernel(const float* __restrict__ src, int64_t src_rows, int C, int ld
 }
 
 constexpr int KP_MAXK = 16;   // kernel points handled (reference configs use 15)
-constexpr int KP_CCH = 128;   // channels per pass (4 per lane)
 
 // One warp per query point.  Lane h (and h+32) computes the 15 influence weights of
-// neighbour h; the warp then walks the neighbours, every lane accumulating its channels.
+// neighbour h; the warp then walks the neighbours, every lane accumulating its channels
+// (NE channels per lane and pass: 1 for Cin <= 32, 2 for <= 64, 4 otherwise).
+template <int NE>
 __global__ void __launch_bounds__(256)
 kpconv_gather_kernel(const float* __restrict__ q_pts, const float* __restrict__ s_pts,
                      int64_t n_support, const void* __restrict__ nidx, int idx_is64, int H,
@@ -65,6 +66,7 @@ kpconv_gather_kernel(const float* __restrict__ q_pts, const float* __restrict__ 
     const float qx = q_pts[3 * q], qy = q_pts[3 * q + 1], qz = q_pts[3 * q + 2];
     const float inv_ext = extent;  // divide, as the reference does
     const int KK = K * Cin;
+    constexpr int KP_CCH = 32 * NE;
     for (int h0 = 0; h0 < H || h0 == 0; h0 += 32) {
         // ---- influence weights of neighbour h0+lane
         float w[KP_MAXK];
@@ -161,10 +163,17 @@ extern "C" int o3dml_kpconv_gather(const float* query_points, int64_t num_querie
                 "kpconv: at most %d kernel points", KP_MAXK);
     O3DML_CHECK(max_neighbors >= 0 && in_channels >= 1 && kp_extent > 0.f, "kpconv: bad sizes");
     if (num_queries <= 0) return O3DML_OK;
-    kpconv_gather_kernel<<<(unsigned)ceil_div<int64_t>(num_queries, 8), 256, 0, (cudaStream_t)stream>>>(
-        query_points, support_points, num_support, neighbor_index, index_is64, max_neighbors,
-        features, in_channels, kernel_points, num_kernel_points, kp_extent, num_queries,
-        weighted_features);
+    const unsigned nb = (unsigned)ceil_div<int64_t>(num_queries, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+#define KP_LAUNCH(NE)                                                                                   \
+    kpconv_gather_kernel<NE><<<nb, 256, 0, st>>>(query_points, support_points, num_support, neighbor_index, \
+                                                 index_is64, max_neighbors, features, in_channels,          \
+                                                 kernel_points, num_kernel_points, kp_extent, num_queries,  \
+                                                 weighted_features)
+    if (in_channels <= 32) KP_LAUNCH(1);
+    else if (in_channels <= 64) KP_LAUNCH(2);
+    else KP_LAUNCH(4);
+#undef KP_LAUNCH
     O3DML_LAUNCH_CHECK();
     o3dml_count_launches(1);
     return O3DML_OK;
