@@ -403,7 +403,21 @@ def run_b200(args, wl):
     # --- e2e
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
-    ms_e2e = timed_region(step_e2e, args.steps, dist_on, dev)
+    ms_e2e_sync = timed_region(step_e2e, args.steps, dist_on, dev)
+    # pipelined public path (open3d_ml_b200.PipelinedRunner): H2D of batch k+1 and D2H of batch k-1
+    # overlap the forward of batch k; every batch's inputs and result still cross PCIe in the region
+    from open3d_ml_b200 import PipelinedRunner
+    runner = PipelinedRunner(model, dev)
+
+    def e2e_stream(n):
+        acc = 0.0
+        for res in runner.run(host_inp for _ in range(n)):
+            r0 = res[0] if isinstance(res, tuple) else res
+            acc += float(r0.view(-1)[0])          # the caller touches every result on the host
+        return acc
+
+    e2e_stream(max(2, args.warmup // 2))
+    ms_e2e = timed_region(lambda: e2e_stream(args.steps), 1, dist_on, dev)
     pts_step = wl.points_per_step() * world
     value = pts_step * args.steps / (ms * 1e-3) / 1e6
     e2e_v = pts_step * args.steps / (ms_e2e * 1e-3) / 1e6
@@ -490,7 +504,9 @@ def run_b200(args, wl):
                             l2="inputs + activations per step (%.0f MB inputs) exceed the 126 MB L2; no flush"
                                % (bi / 1e6)),
                 clocks=clk, e2e=dict(value=round(e2e_v, 3), unit="Mpoints/s", h2d_bytes_per_step=bi,
-                                     d2h_bytes_per_step=bo, ms_per_step=round(ms_e2e / args.steps, 4)),
+                                     d2h_bytes_per_step=bo, ms_per_step=round(ms_e2e / args.steps, 4),
+                                     mode="PipelinedRunner, 2 slots: copies of neighbouring batches overlap the forward",
+                                     sync_value=round(pts_step * args.steps / (ms_e2e_sync * 1e-3) / 1e6, 3)),
                 gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
     if dist_on:

@@ -23,4 +23,7 @@ def __getattr__(name):
     if name in ("KPFCNNB200",):
         from .kpconv import KPFCNNB200
         return KPFCNNB200
+    if name in ("PipelinedRunner",):
+        from .pipeline import PipelinedRunner
+        return PipelinedRunner
     raise AttributeError(name)

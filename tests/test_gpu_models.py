@@ -150,3 +150,24 @@ def test_kpfcnn_medium_vs_port_with_gpu_radius_pyramid():
     with torch.no_grad():
         ref = MT.kpfcnn_forward(sd, tb, extra["cfg"])
     assert out.shape == ref.shape and rel_err(out, ref) < TOL
+
+
+# ------------------------------------------------------------------ pipelined runner
+def test_pipelined_runner_matches_direct_calls():
+    """PipelinedRunner overlaps copies with the forward; results must equal the plain call,
+    batch by batch and in order, including when consecutive batches differ."""
+    sd, _ = H.state_dict("randlanet_semantickitti.manifest.json", 3)
+    net = M.RandLANetB200(sd)
+    batches = [H.randla_inputs(2, 2048, 50 + 10 * i) for i in range(5)]
+    pinned = [{k: ([t.pin_memory() for t in v] if isinstance(v, list) else v.pin_memory())
+               for k, v in b.items()} for b in batches]
+    want = [net(b).cpu().clone() for b in batches]
+    runner = M.PipelinedRunner(net)
+    got = [r.clone() for r in runner.run(iter(pinned))]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+    # second pass reuses the slots
+    got2 = [r.clone() for r in runner.run(iter(pinned[::-1]))]
+    for g, w in zip(got2, want[::-1]):
+        assert torch.equal(g, w)
