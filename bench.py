@@ -304,7 +304,7 @@ def run_reference(args, wl):
                 cpu_baseline=dict(value=round(v, 5), unit="Mpoints/s", cores=torch.get_num_threads(),
                                   kind="port", sample="%d x %d pts, %d steps" % (sample, wl.N, args.steps)),
                 e2e=dict(value=round(v, 5), unit="Mpoints/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -450,7 +450,7 @@ def run_b200(args, wl):
             e[2] += wl.roofline_bytes(d, n)
             e[3] += wl.roofline_flops(d, s, n)
         ach = tot_bytes / (tot_ms * 1e-3) / 1e9
-        roof = dict(bound="hbm", kernel="lfa_pool_tc_kernel, tcgen05 (all 8 launches per step)",
+        roof = dict(bound="hbm", kernel="lfa_pool: tcgen05 lfa_pool_tc_kernel (d>=32) + lfa16_kernel (d=16), all 8 launches per step",
                     achieved=round(ach, 2), peak=pk["hbm_gbs"], unit="GB/s", frac=round(ach / pk["hbm_gbs"], 5),
                     traffic=None, peak_source=pk["src"],
                     share_of_step=round(tot_ms / ms, 4),
@@ -508,12 +508,28 @@ def run_b200(args, wl):
                                      mode="PipelinedRunner, 2 slots: copies of neighbouring batches overlap the forward",
                                      sync_value=round(pts_step * args.steps / (ms_e2e_sync * 1e-3) / 1e6, 3)),
                 gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist_on:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    # libraries (NCCL's version banner, torchrun notices) write to fd 1: keep the original stdout
+    # for the JSON line only and send everything else to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
