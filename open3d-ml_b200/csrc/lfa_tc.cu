@@ -52,17 +52,24 @@ struct LtcCfg {
     static constexpr int H = D / 2;
     static constexpr bool STREAM = D > 128;          // weights do not fit next to the A tile
     static constexpr bool MMA2 = STAGE == 2 && H >= 16;  // lse2 on the tensor core
+    // TRANS: the score GEMM runs transposed (M = score channel, N = neighbour row) and a second,
+    // identity-weight GEMM delivers X^T the same way, so that one thread sees the 16 neighbours
+    // of a (point, channel) in its own TMEM lane: the softmax needs no cross-lane traffic.
+    static constexpr bool TRANS = !STREAM && D >= 64;
+    static constexpr int NTH = (TRANS && D == 128) ? 512 : 256;   // threads per CTA
+    static constexpr int NPART = NTH / LTC_ROWS;                  // threads sharing one row
     static constexpr int A_BYTES = D / 8 * LTC_ROWS * 16;  // one of hi / lo
-    static constexpr int B_BYTES = STREAM ? 0 : D / 8 * D * 16;
+    static constexpr int B_BYTES = STREAM ? 0 : TRANS ? D / 8 * LTC_ROWS * 16 : D / 8 * D * 16;
+    static constexpr int I_BYTES = TRANS ? D / 8 * LTC_ROWS * 16 : 0;   // identity operand (hi only)
     static constexpr int B2_BYTES = (MMA2 && !STREAM) ? H / 8 * H * 16 : 0;
     static constexpr int RING_SLOT = STREAM ? 2 * (LTC_SLICE / 8) * D * 16 : 0;  // hi + lo of one slice
     static constexpr int W10_BYTES = 12 * H * 4;
     static constexpr int ST2_BYTES = STAGE == 2 ? (2 * H + (H < 16 ? H * H : 0)) * 4 : 0;
-    static constexpr int TMEM_NEED = D + (MMA2 ? H : 0);
+    static constexpr int TMEM_NEED = TRANS ? 256 : D + (MMA2 ? H : 0);
     static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128
                                      : TMEM_NEED <= 256 ? 256 : 512;
-    static constexpr size_t SMEM = 2 * A_BYTES + 2 * B_BYTES + 2 * B2_BYTES + 2 * RING_SLOT + W10_BYTES +
-                                   ST2_BYTES + 128;
+    static constexpr size_t SMEM = 2 * A_BYTES + 2 * B_BYTES + I_BYTES + 2 * B2_BYTES + 2 * RING_SLOT +
+                                   W10_BYTES + ST2_BYTES + 128;
 };
 
 // D[tmem_d] = A[128 x K] * B[N x K]^T, all operands resident in shared memory; one thread.
@@ -80,6 +87,22 @@ __device__ __forceinline__ void issue_resident(uint32_t tmem_d, const uint8_t* a
         tc::umma_f16(tmem_d, ah, bh, idesc, ks > 0);
         tc::umma_f16(tmem_d, ah, bl, idesc, 1);
         tc::umma_f16(tmem_d, al, bh, idesc, 1);
+    }
+}
+
+// D[tmem_d][c][row] = X[row][c]: A = identity (128 x K, exact in fp16), B = the X tile (hi + lo).
+template <int K>
+__device__ __forceinline__ void issue_identity(uint32_t tmem_d, const uint8_t* i_hi, const uint8_t* x_hi,
+                                               const uint8_t* x_lo) {
+    constexpr uint32_t idesc = tc::idesc_f16(LTC_ROWS, LTC_ROWS);
+    constexpr uint32_t LBO = LTC_ROWS * 16;
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t ih = tc::smem_desc(tc::smem_u32(i_hi) + ks * 2 * LBO, LBO, 128);
+        const uint64_t xh = tc::smem_desc(tc::smem_u32(x_hi) + ks * 2 * LBO, LBO, 128);
+        const uint64_t xl = tc::smem_desc(tc::smem_u32(x_lo) + ks * 2 * LBO, LBO, 128);
+        tc::umma_f16(tmem_d, ih, xh, idesc, ks > 0);
+        tc::umma_f16(tmem_d, ih, xl, idesc, 1);
     }
 }
 
@@ -150,16 +173,17 @@ __device__ __forceinline__ void gemm_streamed(uint32_t tmem_d, const uint8_t* a_
 }
 
 template <int D, int STAGE>
-__global__ void __launch_bounds__(LTC_THREADS, 1)
+__global__ void __launch_bounds__((LtcCfg<D, STAGE>::NTH), 1)
 lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
     using C = LtcCfg<D, STAGE>;
-    constexpr int H = C::H;
+    constexpr int H = C::H, NTH = C::NTH, NPART = C::NPART;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* a_hi = smem;
     uint8_t* a_lo = a_hi + C::A_BYTES;
     uint8_t* b_hi = a_lo + C::A_BYTES;
     uint8_t* b_lo = b_hi + C::B_BYTES;
-    uint8_t* b2_hi = b_lo + C::B_BYTES;
+    uint8_t* i_hi = b_lo + C::B_BYTES;
+    uint8_t* b2_hi = i_hi + C::I_BYTES;
     uint8_t* b2_lo = b2_hi + C::B2_BYTES;
     uint8_t* ring = b2_lo + C::B2_BYTES;
     float* W10 = reinterpret_cast<float*>(ring + 2 * C::RING_SLOT);  // [12][H]
@@ -169,26 +193,51 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (LTC_ROWS - 1);   // neighbour row of the tile this thread works on
-    const int half = tid >> 7;              // which half of the channels / columns
+    const int half = tid >> 7;              // which part of the channels / columns (0 .. NPART-1)
 
     // ---- once per CTA: weights, barriers, TMEM
-    if (!C::STREAM) {
-        for (int i = tid; i < 2 * C::B_BYTES / 16; i += LTC_THREADS)
+    if (C::TRANS) {
+        // score weight as the M operand: 128 rows (d = 64: the 64 channels twice, so that TMEM lanes
+        // 64..127 serve the second half of the tile's points); source image is [D/8][D][8] hi, lo
+        constexpr int CH = D / 8;
+        for (int i = tid; i < 2 * CH * LTC_ROWS; i += NTH) {
+            const int im = i / (CH * LTC_ROWS), rem = i % (CH * LTC_ROWS);
+            const int kc = rem / LTC_ROWS, r = rem % LTC_ROWS;
+            reinterpret_cast<uint4*>(b_hi)[i] = p.ws_img[(size_t)im * CH * D + kc * D + (r % D)];
+        }
+        for (int i = tid; i < CH * LTC_ROWS; i += NTH) {
+            const int kc = i / LTC_ROWS, r = i % LTC_ROWS;
+            const int j = (r % D) - kc * 8;        // position of the one inside this 8-wide chunk
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (j >= 0 && j < 8) {
+                const uint32_t one = 0x3C00u << ((j & 1) * 16);
+                if ((j >> 1) == 0) v.x = one;
+                else if ((j >> 1) == 1) v.y = one;
+                else if ((j >> 1) == 2) v.z = one;
+                else v.w = one;
+            }
+            reinterpret_cast<uint4*>(i_hi)[i] = v;
+        }
+        if (C::MMA2)
+            for (int i = tid; i < 2 * C::B2_BYTES / 16; i += NTH)
+                reinterpret_cast<uint4*>(b2_hi)[i] = p.wl2_img[i];
+    } else if (!C::STREAM) {
+        for (int i = tid; i < 2 * C::B_BYTES / 16; i += NTH)
             reinterpret_cast<uint4*>(b_hi)[i] = p.ws_img[i];
         if (C::MMA2)
-            for (int i = tid; i < 2 * C::B2_BYTES / 16; i += LTC_THREADS)
+            for (int i = tid; i < 2 * C::B2_BYTES / 16; i += NTH)
                 reinterpret_cast<uint4*>(b2_hi)[i] = p.wl2_img[i];
     }
     if (STAGE == 2) {
-        for (int i = tid; i < H; i += LTC_THREADS) {
+        for (int i = tid; i < H; i += NTH) {
             ST2[i] = p.s2[i];
             ST2[H + i] = p.t2[i];
         }
         if (H < 16)
-            for (int i = tid; i < H * H; i += LTC_THREADS) ST2[2 * H + i] = p.wl2t[i];
+            for (int i = tid; i < H * H; i += NTH) ST2[2 * H + i] = p.wl2t[i];
     }
-    for (int i = tid; i < 10 * H; i += LTC_THREADS) W10[i] = p.w10t[i];
-    for (int i = tid; i < H; i += LTC_THREADS) {
+    for (int i = tid; i < 10 * H; i += NTH) W10[i] = p.w10t[i];
+    for (int i = tid; i < H; i += NTH) {
         W10[10 * H + i] = p.s10[i];
         W10[11 * H + i] = p.t10[i];
     }
@@ -205,6 +254,8 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tmem_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    // TRANS: the lse2 accumulator aliases the score columns (it is consumed before they are written)
+    constexpr int LSE2_COL = C::TRANS ? 0 : D;
     uint32_t ph_main[2] = {0, 0};  // parities of mbar[0] (lse2) and mbar[1] (scores)
     uint32_t ph_ring[2] = {0, 0};  // parities of mbar[2], mbar[3] (weight ring)
 
@@ -230,15 +281,23 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
         //   stage 1            -> channels [H, D) of A
         //   stage 2, tensor    -> channels [0, H) of A (A operand of the lse2 GEMM)
         //   stage 2, H < 16    -> r2 = lrelu(BN(Wl2 . r1)) in registers -> channels [H, D)
-        for (int ch = half; ch < H / 8; ch += 2) {
+        for (int ch = half; ch < H / 8; ch += NPART) {
             float r[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 10; ++q) {   // warp-uniform LDS.128 of the weights
+                const float4 wa = *reinterpret_cast<const float4*>(&W10[q * H + ch * 8]);
+                const float4 wb = *reinterpret_cast<const float4*>(&W10[q * H + ch * 8 + 4]);
+                r[0] = fmaf(e[q], wa.x, r[0]); r[1] = fmaf(e[q], wa.y, r[1]);
+                r[2] = fmaf(e[q], wa.z, r[2]); r[3] = fmaf(e[q], wa.w, r[3]);
+                r[4] = fmaf(e[q], wb.x, r[4]); r[5] = fmaf(e[q], wb.y, r[5]);
+                r[6] = fmaf(e[q], wb.z, r[6]); r[7] = fmaf(e[q], wb.w, r[7]);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int o = ch * 8 + j;
-                float a = 0.f;
-#pragma unroll
-                for (int q = 0; q < 10; ++q) a = fmaf(e[q], W10[q * H + o], a);
-                a = fmaf(a, W10[10 * H + o], W10[11 * H + o]);
+                const float a = fmaf(r[j], W10[10 * H + o], W10[11 * H + o]);
                 r[j] = a >= 0.f ? a : 0.2f * a;
             }
             int dst_chunk = H / 8 + ch;
@@ -272,19 +331,19 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
             __syncthreads();
             tc::tc_fence_after();
             if (C::STREAM) {
-                gemm_streamed<H, H>(tmem + D, a_hi, a_lo, p.wl2_img, ring, C::RING_SLOT, &mbar[2], ph_ring, tid);
+                gemm_streamed<H, H>(tmem + LSE2_COL, a_hi, a_lo, p.wl2_img, ring, C::RING_SLOT, &mbar[2], ph_ring, tid);
             } else {
                 if (tid == 0) {
-                    issue_resident<H, H>(tmem + D, a_hi, a_lo, b2_hi, b2_lo);
+                    issue_resident<H, H>(tmem + LSE2_COL, a_hi, a_lo, b2_hi, b2_lo);
                     tc::umma_commit(&mbar[0]);
                 }
                 tc::mbar_wait(&mbar[0], ph_main[0]);
                 ph_main[0] ^= 1;
                 tc::tc_fence_after();
             }
-            for (int c0 = half * 8; c0 < H; c0 += 16) {
+            for (int c0 = half * 8; c0 < H; c0 += 8 * NPART) {
                 float v[8];
-                tc::tmem_ld8(tmem_lane + D + c0, v);
+                tc::tmem_ld8(tmem_lane + LSE2_COL + c0, v);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float a = fmaf(v[j], ST2[c0 + j], ST2[H + c0 + j]);
@@ -298,7 +357,7 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
         }
         // ---------------- gathered neighbour features -> channels [0, H)  (overwrites r1 in stage 2:
         // the lse2 MMAs that read it have completed)
-        for (int ch = half; ch < H / 8; ch += 2) {
+        for (int ch = half; ch < H / 8; ch += NPART) {
             float x[8];
             if (nb >= 0) {
                 const float4 v0 = *reinterpret_cast<const float4*>(p.feat + (size_t)nb * H + ch * 8);
@@ -324,7 +383,12 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
             gemm_streamed<D, D>(tmem, a_hi, a_lo, p.ws_img, ring, C::RING_SLOT, &mbar[2], ph_ring, tid);
         } else {
             if (tid == 0) {
-                issue_resident<D, D>(tmem, a_hi, a_lo, b_hi, b_lo);
+                if (C::TRANS) {
+                    issue_resident<LTC_ROWS, D>(tmem, b_hi, b_lo, a_hi, a_lo);   // [channel][row]
+                    issue_identity<D>(tmem + LTC_ROWS, i_hi, a_hi, a_lo);        // X^T
+                } else {
+                    issue_resident<D, D>(tmem, a_hi, a_lo, b_hi, b_lo);
+                }
                 tc::umma_commit(&mbar[1]);
             }
             tc::mbar_wait(&mbar[1], ph_main[1]);
@@ -333,9 +397,34 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
         }
 
         // ---------------- softmax over the 16 rows of each point + weighted sum
+        if (C::TRANS) {
+            // thread = TMEM lane = score channel; its 2 points' 16 neighbours are 16 columns each
+            const int tl = (warp & 3) * 32 + lane;
+            const int c = tl % D;
+            const int pbase = (D == 64 ? (tl >> 6) * 4 : 0) + (warp >> 2) * 2;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int pt = pbase + q;
+                float s[16], x[16];
+                tc::tmem_ld16(tmem_lane + pt * LTC_K, s);
+                tc::tmem_ld16(tmem_lane + LTC_ROWS + pt * LTC_K, x);
+                float m = s[0];
+#pragma unroll
+                for (int j = 1; j < 16; ++j) m = fmaxf(m, s[j]);
+                float num = 0.f, den = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float ev = __expf(s[j] - m);
+                    den += ev;
+                    num = fmaf(ev, x[j], num);
+                }
+                const int64_t gp = tile * (LTC_ROWS / LTC_K) + pt;
+                if (gp < p.total) p.agg[(size_t)gp * D + c] = num / den;
+            }
+        }
         const bool upper = (lane & 16) != 0;
         const int j16 = lane & 15;
-        for (int c0 = half * 16; c0 < D; c0 += 32) {
+        for (int c0 = half * 16; c0 < (C::TRANS ? 0 : D); c0 += 32) {
             float s[16], x[16];
             tc::tmem_ld16(tmem_lane + c0, s);
 #pragma unroll
@@ -411,7 +500,7 @@ static int lfa_tc_launch(const LfaTcParams& p, cudaStream_t st) {
     if (per_sm > 4) per_sm = 4;
     int64_t grid = (int64_t)kNumSMs * per_sm;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    lfa_pool_tc_kernel<D, STAGE><<<(unsigned)grid, LTC_THREADS, C::SMEM, st>>>(p);
+    lfa_pool_tc_kernel<D, STAGE><<<(unsigned)grid, C::NTH, C::SMEM, st>>>(p);
     O3DML_LAUNCH_CHECK();
     o3dml_count_launches(1);
     return O3DML_OK;
