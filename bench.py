@@ -56,34 +56,49 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """Launches the sampler and waits for its first row (nvidia-smi needs ~0.1-1 s to come up;
+        the timed region of a fast workload is shorter than that)."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "10"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 5.0:
+                time.sleep(0.01)
         except Exception:  # noqa: BLE001
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self):
+        self.t_end = time.perf_counter()
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) == 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) == 6 and r[1].replace(".", "").isdigit()]
+        lo = (self.t_begin or 0.0) - 0.005
+        rows = [r for t, r in self.rows if lo <= t <= self.t_end + 0.015 and len(r) == 6]
+        window = "timed region"
+        if not rows:   # region shorter than the sampling period: take the rows around it
+            rows = [r for t, r in self.rows if t >= lo - 0.25 and len(r) == 6]
+            window = "timed region +-0.25 s"
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) == 6
-                          for n, v in zip(names, r[2:]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[2:]) if v.lower().startswith("active")})
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=reasons, samples=len(sm))
+                    reasons=reasons, samples=len(sm), window=window)
 
 
 def pin(t):
@@ -390,6 +405,11 @@ def run_b200(args, wl):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(2):           # the GPU idled while the sampler came up: re-warm the clocks
+        step_resident()
+    timers.clear(), dense_timers.clear()
+    if rank == 0:
+        clocks.begin()
     launches0 = L.lib().o3dml_launch_count()
     torch.cuda.cudart().cudaProfilerStart()      # ncu --profile-from-start off sees only the timed steps
     ms = timed_region(step_resident, args.steps, dist_on, dev)

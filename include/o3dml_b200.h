@@ -194,6 +194,18 @@ O3DML_API int o3dml_randla_lfa_pool(int stage, int d, const float* coords, const
                           const float* t10, const float* wl2_t, const float* s2, const float* t2,
                           const float* wscore_t, const float* bscore, float* agg, void* stream);
 
+/* d = 16 variant of o3dml_randla_lfa_pool (the first, largest RandLA-Net level) that takes the
+ * layer's weights from HOST memory, packed as O3DML_LFA16_WEIGHT_FLOATS floats:
+ *   [0,80) w10_t [10][8] | [80,88) s10 | [88,96) t10 | [96,160) wl2_t [8][8] | [160,168) s2 |
+ *   [168,176) t2 | [176,432) wscore_t [16][16] | [432,448) bscore        (all [in][out])
+ * They travel in the kernel parameter block, so every FMA reads its weight as a constant-bank
+ * operand (no shared-memory broadcast loads).  Stage 1 ignores the wl2/s2/t2 fields. */
+#define O3DML_LFA16_WEIGHT_FLOATS 448
+O3DML_API int o3dml_randla_lfa16_pool(int stage, const float* coords, const void* neighbor_idx, int idx_is64,
+                                      int num_neighbors, const float* feat, int64_t batch,
+                                      int64_t n_per_batch, const float* host_weights, float* agg,
+                                      void* stream);
+
 /* Tensor-core (tcgen05, 3xFP16 split) variant of o3dml_randla_lfa_pool, same contract, d in
  * {16, 32, 64, 128, 256}.  wscore_image / wl2_image: the weight [out][in] packed by the host as
  * fp16 hi/lo operand images in the UMMA chunk-major layout ([in/8][out][8 halves] hi, then the

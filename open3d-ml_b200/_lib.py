@@ -47,6 +47,7 @@ _SIGNATURES = {
     "o3dml_conv3x3_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, I, P, P, I, F, P, I, P]),
     "o3dml_deconv_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, I, P, P, I, F, P, I, I, P]),
     "o3dml_randla_lfa_pool": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
+    "o3dml_randla_lfa16_pool": (I, [I, P, P, I, I, P, L, L, P, P, P]),
     "o3dml_randla_lfa_pool_tc": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
     "o3dml_gather_max": (I, [P, L, I, I, P, I, L, I, L, L, I, P, I, P]),
     "o3dml_kpconv_gather": (I, [P, L, P, L, P, I, I, P, I, P, I, F, P, P]),

@@ -172,6 +172,12 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 #ifdef O3DML_DEBUG_TIMING
     const bool dbg = blockIdx.x == 0 && blockIdx.y == 0;
     if (dbg && tid == 0) g_gt_dbg[4000] = clock64();
+    const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0 && cta_lin < 1000) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_gt_dbg[5000 + cta_lin] = (long long)gt;
+    }
 #endif
 
     // ---- per-row gather bookkeeping
@@ -243,8 +249,13 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         return base ? base + (k - p.koff[sidx]) : nullptr;
     };
 
-    float a_scale, out_scale;
-    {   // ---- range pass: max |A| over this CTA's tile -> exact power-of-two scale (all threads)
+    float a_scale = 1.f, out_scale = 1.f;
+    // ---- range pass: max |A| over this CTA's tile -> exact power-of-two scale.  Only the converter
+    // warps (the consumers of a_scale / out_scale) take part, on their own named barrier: the MMA warp
+    // starts the weight-slice bulk copies and the loader warps the first GT_STAGES slices of A meanwhile.
+    constexpr int RT = 2 * GT_CONV;                       // range threads
+    if (tid >= GT_THREADS - RT) {
+        const int rtid = tid - (GT_THREADS - RT);
         float mx = 0.f;
         if (p.mode == 1) {
             // conv: every tap of every row lies in ONE contiguous pixel span of the NHWC input (a superset
@@ -261,22 +272,22 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             int64_t hi = min(tot_pix - 1, in_pix(n_last, 2, 2));
             const float4* base = reinterpret_cast<const float4*>(p.src[0].data + lo * p.C);
             const int64_t n4 = (hi - lo + 1) * p.C / 4;
-            for (int64_t i = tid; i < n4; i += 4 * GT_THREADS) {
+            for (int64_t i = rtid; i < n4; i += 4 * RT) {
                 float4 v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    v[u] = (i + u * GT_THREADS < n4) ? base[i + u * GT_THREADS] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[u] = (i + u * RT < n4) ? base[i + u * RT] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[u].x), fabsf(v[u].y)), fmaxf(fabsf(v[u].z), fabsf(v[u].w))));
             }
         } else {
             const int total = nsl * (GT_ROWS * GT_CH);            // (slice, row, chunk) items
-            for (int i0 = tid; i0 < total; i0 += 4 * GT_THREADS) {
+            for (int i0 = rtid; i0 < total; i0 += 4 * RT) {
                 float4 v[4][2];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {                      // 4 independent gathers in flight per thread
-                    const int i = i0 + u * GT_THREADS;
+                    const int i = i0 + u * RT;
                     const float* src = nullptr;
                     if (i < total) {
                         const int s = i / (GT_ROWS * GT_CH), rem = i - s * (GT_ROWS * GT_CH);
@@ -294,11 +305,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             }
         }
         const unsigned wmx = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));  // mx >= 0: bits are ordered
-        if ((tid & 31) == 0) amax_warp[tid >> 5] = wmx;
-        __syncthreads();
+        if ((rtid & 31) == 0) amax_warp[rtid >> 5] = wmx;
+        asm volatile("bar.sync 1, %0;" ::"n"(RT) : "memory");
         unsigned bm = 0;
 #pragma unroll
-        for (int i = 0; i < GT_THREADS / 32; ++i) bm = max(bm, amax_warp[i]);
+        for (int i = 0; i < RT / 32; ++i) bm = max(bm, amax_warp[i]);
         const float amax = __uint_as_float(bm);
         int e = 0;
         if (amax > 0.f && amax < 3.0e38f) e = 13 - ilogbf(amax);   // amax * 2^e in [2^13, 2^14)
@@ -623,6 +634,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     __syncthreads();
 #ifdef O3DML_DEBUG_TIMING
     if (dbg && tid == 0) g_gt_dbg[4003] = clock64();
+    if (tid == 0 && cta_lin < 1000) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        g_gt_dbg[6000 + cta_lin] = (long long)gt;
+    }
 #endif
     if (warp == 0) tc::tmem_dealloc<C::TMEM_COLS>(tmem);
 }

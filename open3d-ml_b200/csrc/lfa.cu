@@ -22,6 +22,7 @@
 // variant plugs into the same tiles.
 #include "../../include/o3dml_b200.h"
 #include "common.cuh"
+#include <string.h>
 
 namespace o3dml {
 
@@ -439,6 +440,129 @@ static int lfa16_launch(const LfaParams& p, cudaStream_t st) {
     return O3DML_OK;
 }
 
+// Same kernel with the layer's weights in the KERNEL PARAMETER block (constant bank 0): every
+// FFMA takes its weight as a c[0][imm] operand, so no instruction and no register-file write
+// is spent on loading weights.  (ncu on lfa16_kernel: 110 warp-uniform LDS.128 per row =
+// 440 cycles of shared-memory return path per warp vs 206 issue cycles -> that kernel is bound
+// by the broadcast writes, not by the FMAs.)  The host passes the packed weights from HOST memory.
+struct alignas(16) Lfa16W {
+    float v[O3DML_LFA16_WEIGHT_FLOATS];
+};
+constexpr int W16_W10 = 0, W16_S10 = 80, W16_T10 = 88, W16_WL2 = 96, W16_S2 = 160, W16_T2 = 168,
+              W16_WS = 176, W16_BS = 432;
+
+template <int STAGE>
+__global__ void __launch_bounds__(L16_ROWS, 4)
+lfa16c_kernel(const __grid_constant__ LfaParams p, const __grid_constant__ Lfa16W w, int64_t num_groups) {
+    constexpr int D = 16, H = 8;
+    __shared__ __align__(16) float St[D * L16_RS];      // scores, channel-major
+    __shared__ __align__(16) float Xs[D * L16_RS];      // X, channel-major
+    const int tid = threadIdx.x;
+    const int pl = tid >> 4, j = tid & 15;
+    for (int64_t grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
+        const int64_t g = grp * L16_PTS + pl;
+        float x[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) x[c] = 0.f;
+        if (g < p.total) {
+            const int64_t b = g / p.n_per_batch;
+            const int64_t gn = b * p.n_per_batch + load_index(p.nidx, g * LFA_K + j, p.nidx_is64);
+            const float4 f0 = *reinterpret_cast<const float4*>(p.feat + (size_t)gn * H);
+            const float4 f1 = *reinterpret_cast<const float4*>(p.feat + (size_t)gn * H + 4);
+            const float qx = p.coords[3 * g], qy = p.coords[3 * g + 1], qz = p.coords[3 * g + 2];
+            const float cx = p.coords[3 * gn], cy = p.coords[3 * gn + 1], cz = p.coords[3 * gn + 2];
+            const float dx = qx - cx, dy = qy - cy, dz = qz - cz;
+            float e[10];
+            e[0] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+            e[1] = dx; e[2] = dy; e[3] = dz;
+            e[4] = qx; e[5] = qy; e[6] = qz;
+            e[7] = cx; e[8] = cy; e[9] = cz;
+            x[0] = f0.x; x[1] = f0.y; x[2] = f0.z; x[3] = f0.w;
+            x[4] = f1.x; x[5] = f1.y; x[6] = f1.z; x[7] = f1.w;
+            float r1[H];
+#pragma unroll
+            for (int o = 0; o < H; ++o) r1[o] = 0.f;
+#pragma unroll
+            for (int q = 0; q < 10; ++q)      // weight rows are consumed contiguously -> LDCU.128
+#pragma unroll
+                for (int o = 0; o < H; ++o) r1[o] = fmaf(e[q], w.v[W16_W10 + q * H + o], r1[o]);
+#pragma unroll
+            for (int o = 0; o < H; ++o) {
+                const float a = fmaf(r1[o], w.v[W16_S10 + o], w.v[W16_T10 + o]);
+                r1[o] = a >= 0.f ? a : 0.2f * a;
+            }
+            if (STAGE == 1) {
+#pragma unroll
+                for (int o = 0; o < H; ++o) x[H + o] = r1[o];
+            } else {
+                float r2[H];
+#pragma unroll
+                for (int o = 0; o < H; ++o) r2[o] = 0.f;
+#pragma unroll
+                for (int k = 0; k < H; ++k)
+#pragma unroll
+                    for (int o = 0; o < H; ++o) r2[o] = fmaf(r1[k], w.v[W16_WL2 + k * H + o], r2[o]);
+#pragma unroll
+                for (int o = 0; o < H; ++o) {
+                    const float a = fmaf(r2[o], w.v[W16_S2 + o], w.v[W16_T2 + o]);
+                    x[H + o] = a >= 0.f ? a : 0.2f * a;
+                }
+            }
+        }
+        float sc[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) sc[c] = w.v[W16_BS + c];
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int c = 0; c < D; ++c) sc[c] = fmaf(x[k], w.v[W16_WS + k * D + c], sc[c]);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            St[c * L16_RS + tid] = sc[c];
+            Xs[c * L16_RS + tid] = x[c];
+        }
+        __syncthreads();
+        {
+            const float* srow = St + j * L16_RS + pl * LFA_K;
+            const float* xrow = Xs + j * L16_RS + pl * LFA_K;
+            float4 s4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s4[q] = *reinterpret_cast<const float4*>(srow + 4 * q);
+            float m = s4[0].x;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) m = fmaxf(fmaxf(fmaxf(m, s4[q].x), s4[q].y), fmaxf(s4[q].z, s4[q].w));
+            float num = 0.f, den = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 xv = *reinterpret_cast<const float4*>(xrow + 4 * q);
+                const float e0 = expf(s4[q].x - m), e1 = expf(s4[q].y - m);
+                const float e2 = expf(s4[q].z - m), e3 = expf(s4[q].w - m);
+                den += (e0 + e1) + (e2 + e3);
+                num = fmaf(e0, xv.x, num);
+                num = fmaf(e1, xv.y, num);
+                num = fmaf(e2, xv.z, num);
+                num = fmaf(e3, xv.w, num);
+            }
+            if (g < p.total) p.agg[(size_t)g * D + j] = num / den;
+        }
+        __syncthreads();
+    }
+}
+
+template <int STAGE>
+static int lfa16c_launch(const LfaParams& p, const Lfa16W& w, cudaStream_t st) {
+    const int64_t groups = ceil_div<int64_t>(p.total, L16_PTS);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t cap = (int64_t)sms * 4;
+    const unsigned blocks = (unsigned)(groups < cap ? groups : cap);
+    lfa16c_kernel<STAGE><<<blocks, L16_ROWS, 0, st>>>(p, w, groups);
+    O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
+    return O3DML_OK;
+}
+
 }  // namespace o3dml
 
 using namespace o3dml;
@@ -479,4 +603,29 @@ extern "C" int o3dml_randla_lfa_pool(int stage, int d, const float* coords, cons
             O3DML_FAIL(O3DML_ERR_UNSUPPORTED, "lfa: d_out %d not in {16,32,64,128,256}", d);
     }
 #undef LFA_CASE
+}
+
+extern "C" int o3dml_randla_lfa16_pool(int stage, const float* coords, const void* neighbor_idx, int idx_is64,
+                                       int num_neighbors, const float* feat, int64_t batch,
+                                       int64_t n_per_batch, const float* host_weights, float* agg,
+                                       void* stream) {
+    O3DML_CHECK(stage == 1 || stage == 2, "lfa16: stage must be 1 or 2");
+    O3DML_CHECK(num_neighbors == LFA_K, "lfa16: the fused kernel is built for 16 neighbours");
+    O3DML_CHECK(batch * n_per_batch < ((int64_t)1 << 31), "lfa16: too many points");
+    O3DML_CHECK(host_weights != nullptr, "lfa16: host_weights is null");
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host_weights) == cudaSuccess)
+        O3DML_CHECK(attr.type != cudaMemoryTypeDevice, "lfa16: host_weights must point to HOST memory");
+    else
+        cudaGetLastError();
+    LfaParams p;
+    p.coords = coords; p.nidx = neighbor_idx; p.nidx_is64 = idx_is64; p.feat = feat;
+    p.total = batch * n_per_batch; p.n_per_batch = n_per_batch;
+    p.w10t = p.s10 = p.t10 = p.wl2t = p.s2 = p.t2 = p.wst = p.bs = nullptr;
+    p.agg = agg;
+    if (p.total == 0) return O3DML_OK;
+    Lfa16W w;
+    memcpy(w.v, host_weights, sizeof(w.v));
+    cudaStream_t st = (cudaStream_t)stream;
+    return stage == 1 ? lfa16c_launch<1>(p, w, st) : lfa16c_launch<2>(p, w, st);
 }

@@ -85,6 +85,18 @@ class RandLANetB200:
                         sd["%s.%s.score_fn.0.weight" % (p, pool)])
                 if d >= 32:
                     self.w[p + ".lse2.mlp.img"] = L.pack_operand_image(sd[p + ".lse2.mlp.conv.weight"][:, :, 0, 0])
+            if d == 16:   # lfa16c_kernel: weights travel in the kernel parameter block (HOST memory)
+                for stage, pool in ((1, "pool1"), (2, "pool2")):
+                    hw = torch.zeros(448, dtype=torch.float32)
+                    hw[0:80] = self.w[p + ".lse1.mlp.wt"].cpu().reshape(-1)
+                    hw[80:88] = self.w[p + ".lse1.mlp.s"].cpu()
+                    hw[88:96] = self.w[p + ".lse1.mlp.t"].cpu()
+                    hw[96:160] = self.w[p + ".lse2.mlp.wt"].cpu().reshape(-1)
+                    hw[160:168] = self.w[p + ".lse2.mlp.s"].cpu()
+                    hw[168:176] = self.w[p + ".lse2.mlp.t"].cpu()
+                    hw[176:432] = self.w["%s.%s.score.wt" % (p, pool)].cpu().reshape(-1)
+                    hw[432:448] = self.w["%s.%s.score.b" % (p, pool)].cpu()
+                    self.w["%s.lfa16.%d" % (p, stage)] = hw.contiguous()
             # mlp2 + shortcut as ONE gemm over [p2 | feat] with the BN scales folded into the rows
             s2, t2 = _fold_bn(sd, p + ".mlp2.batch_norm", sd[p + ".mlp2.conv.bias"])
             ss, ts = _fold_bn(sd, p + ".shortcut.batch_norm", sd[p + ".shortcut.conv.bias"])
@@ -128,6 +140,11 @@ class RandLANetB200:
                 L.ptr(w[p + ".lse2.mlp.s"]) if stage == 2 else None,
                 L.ptr(w[p + ".lse2.mlp.t"]) if stage == 2 else None,
                 L.ptr(w["%s.%s.score.img" % (p, pool)]), L.ptr(agg), L.stream()))
+            return
+        if d == 16 and self.use_tc:
+            L.check(L.lib().o3dml_randla_lfa16_pool(
+                stage, L.ptr(coords), L.ptr(nidx), 1 if nidx.dtype == torch.int64 else 0, self.k,
+                L.ptr(feat), B, N, w["%s.lfa16.%d" % (p, stage)].data_ptr(), L.ptr(agg), L.stream()))
             return
         L.check(L.lib().o3dml_randla_lfa_pool(
             stage, d, L.ptr(coords), L.ptr(nidx), 1 if nidx.dtype == torch.int64 else 0, self.k,
