@@ -40,6 +40,9 @@ O3DML_API int o3dml_abi_version(void);
 O3DML_API const char* o3dml_last_error(void);
 /* number of CUDA kernels this library has enqueued in the process (bench.py: gpu_launches) */
 O3DML_API unsigned long long o3dml_launch_count(void);
+/* a host that replays kernels of this library from a captured CUDA graph reports them here
+ * (the counter above only sees direct launches) */
+O3DML_API void o3dml_launch_count_add(unsigned long long n);
 
 /* ------------------------------------------------------------------ ops ---- */
 
@@ -181,6 +184,20 @@ O3DML_API int o3dml_deconv_nhwc_tc(const float* in, int batch, int H, int W, int
                               const float* scale,
                                    const float* shift, int act, float slope, float* out, int out_ld,
                                    int out_channels, void* stream);
+
+/* Narrow per-point dense layer, one thread per row (rowmlp.cu): same contract as o3dml_linear
+ * for 1 or 2 sources (the second may be gathered) without residual / NCHW output, for the
+ * (channels0, channels1, out_channels) triples listed in csrc/rowmlp_shapes.inc
+ * (o3dml_linear_rows_small_supported returns 1 for those).  weight_t [K, out_channels], scale and
+ * shift (may be NULL) are read from HOST memory at call time and travel in the kernel parameter
+ * block, so every multiply takes its weight from the constant bank: these layers
+ * (SharedMLPs of RandLA-Net's first level and classifier, randlanet.py:110-113, :653-664) are
+ * HBM-bound and need neither shared memory nor barriers. */
+O3DML_API int o3dml_linear_rows_small_supported(int channels0, int channels1, int out_channels);
+O3DML_API int o3dml_linear_rows_small(int64_t num_rows, const o3dml_src_t* srcs, int num_srcs,
+                                      const float* host_weight_t, const float* host_scale,
+                                      const float* host_shift, int act, float slope, float* out, int out_ld,
+                                      int out_channels, void* stream);
 
 /* ---------------------------------------------------------- RandLA-Net ---- */
 

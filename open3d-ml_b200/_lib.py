@@ -30,6 +30,7 @@ _SIGNATURES = {
     "o3dml_abi_version": (c_int, []),
     "o3dml_last_error": (ctypes.c_char_p, []),
     "o3dml_launch_count": (ctypes.c_ulonglong, []),
+    "o3dml_launch_count_add": (None, [ctypes.c_ulonglong]),
     "o3dml_voxelize_workspace_bytes": (Z, [L, L]),
     "o3dml_voxelize": (I, [P, L, I, P, L, P, P, P, L, L, P, P, P, P, P, P, P, Z, P]),
     "o3dml_ragged_to_dense": (I, [P, I, L, P, L, L, L, L, P, P]),
@@ -47,6 +48,8 @@ _SIGNATURES = {
     "o3dml_conv3x3_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, I, P, P, I, F, P, I, P]),
     "o3dml_deconv_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, I, P, P, I, F, P, I, I, P]),
     "o3dml_randla_lfa_pool": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
+    "o3dml_linear_rows_small_supported": (I, [I, I, I]),
+    "o3dml_linear_rows_small": (I, [L, P, I, P, P, P, I, F, P, I, I, P]),
     "o3dml_randla_lfa16_pool": (I, [I, P, P, I, I, P, L, L, P, P, P]),
     "o3dml_randla_lfa_pool_tc": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
     "o3dml_gather_max": (I, [P, L, I, I, P, I, L, I, L, L, I, P, I, P]),
@@ -139,6 +142,18 @@ class PackedWeight:
         wp = torch.zeros((self.n_pad, self.k_pad), dtype=torch.float32)
         wp[:self.cout, :self.k] = w.t() * (2.0 ** self.w_exp)
         self.img = pack_operand_image(wp)
+        self.host = w                      # fp32 [K, Cout] on the host: rowmlp.cu takes it by value
+        self._host_affine = {}
+
+    def host_affine(self, scale, shift):
+        """Host copies of the folded-BN scale / shift of this layer (made once, at first use)."""
+        key = (0 if scale is None else scale.data_ptr(), 0 if shift is None else shift.data_ptr())
+        ent = self._host_affine.get(key)
+        if ent is None:
+            ent = (None if scale is None else scale.detach().float().cpu().contiguous(),
+                   None if shift is None else shift.detach().float().cpu().contiguous())
+            self._host_affine[key] = ent
+        return ent
 
     @property
     def shape(self):
@@ -161,6 +176,17 @@ def _tc_ok(srcs):
     return all((s.channels % 8 == 0) and (s.ld % 4 == 0) and (s.data % 16 == 0) for s in srcs)
 
 
+USE_ROW_MLP = os.environ.get("O3DML_ROW_MLP", "1") != "0"
+
+
+def _rows_small_ok(srcs, out, ld, co):
+    """Alignment contract of rowmlp.cu: float4 access wherever a width is a multiple of 4."""
+    for s in srcs:
+        if s.channels % 4 == 0 and (s.ld % 4 or s.data % 16):
+            return False
+    return not (co % 4 == 0 and (ld % 4 or out.data_ptr() % 16))
+
+
 def linear(srcs, weight, out, scale=None, shift=None, residual=None, act=None, slope=0.0,
            num_rows=None, out_channels=None, out_ld=None, out_nchw_plane=0):
     """out[n,:] = act(scale * (concat(srcs)[n] @ W) + shift + residual[n]).  `weight` is either an
@@ -173,7 +199,13 @@ def linear(srcs, weight, out, scale=None, shift=None, residual=None, act=None, s
     co = wt.shape[1] if out_channels is None else out_channels
     ld = (out.stride(0) if out_nchw_plane == 0 else co) if out_ld is None else out_ld
     res_ld = residual.stride(0) if residual is not None else 0
-    if packed and _tc_ok(srcs):
+    if (packed and USE_ROW_MLP and residual is None and out_nchw_plane == 0 and len(srcs) <= 2 and
+            lib().o3dml_linear_rows_small_supported(srcs[0].channels, srcs[1].channels if len(srcs) == 2 else 0,
+                                                    co) and _rows_small_ok(srcs, out, ld, co)):
+        hs, ht = weight.host_affine(scale, shift)
+        check(lib().o3dml_linear_rows_small(n, arr, len(srcs), weight.host.data_ptr(), ptr(hs), ptr(ht),
+                                            act_code(act), float(slope), ptr(out), ld, co, stream()))
+    elif packed and _tc_ok(srcs):
         check(lib().o3dml_linear_tc(n, arr, len(srcs), ptr(weight.img), weight.k_pad, weight.n_pad, weight.w_exp,
                                     ptr(scale), ptr(shift), ptr(residual), res_ld, act_code(act),
                                     float(slope), ptr(out), ld, co, out_nchw_plane, stream()))

@@ -17,4 +17,5 @@ extern "C" int o3dml_abi_version(void) { return O3DML_ABI_VERSION; }
 
 static std::atomic<unsigned long long> g_launches{0};
 extern "C" void o3dml_count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+extern "C" void o3dml_launch_count_add(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" unsigned long long o3dml_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

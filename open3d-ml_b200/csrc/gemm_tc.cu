@@ -571,8 +571,15 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
 #ifdef O3DML_DEBUG_TIMING
         if (dbg && rt == 0 && grp == 0) g_gt_dbg[4002] = clock64();
 #endif
-        // ---- epilogue: thread = output row, this group's column half, 16 columns at a time
+        // ---- epilogue: thread = output row, this group's column half, 16 columns at a time.
+        // Row-major and pixel-shuffle outputs are staged through the (now dead) pipeline stages so that the
+        // global stores are whole rows written by consecutive lanes: with thread = row, one store
+        // instruction touched 32 different rows (32 half-filled sectors; 154 us for the 53 k-row K = 64
+        // deconvolution of the PointPillars neck).
         const int64_t n = row0 + rt;
+        constexpr int SLD = BN + 4;                                  // staging row stride (floats)
+        float* stg = reinterpret_cast<float*>(stages);
+        const bool staged = p.out_mode == 0 || (p.out_mode == 2 && (p.dC & 3) == 0);
         if (owns_cols) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
@@ -591,7 +598,12 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                         v[j] = apply_act(x, p.act, p.slope);
                     }
                 }
-                if (p.out_mode == 0) {
+                if (staged) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        *reinterpret_cast<float4*>(stg + rt * SLD + c0 + 4 * u) =
+                            make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                } else if (p.out_mode == 0) {
                     float* o = p.out + (size_t)n * p.out_ld + cbase;
                     if (cbase + 15 < p.Cout && (p.out_ld & 3) == 0 &&
                         ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) {
@@ -625,6 +637,42 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                                                 (size_t)ix * p.ds + dx;
                             p.out[opix * p.out_ld + co] = v[j];
                         }
+                    }
+                }
+            }
+        }
+        if (staged) {
+            named_bar_sync(2, 2 * GT_CONV);                            // the 8 epilogue warps
+            constexpr int LPR = BN / 4;                                // lanes per output row
+            const int et = grp * GT_CONV + rt;                         // 0 .. 255
+            const int c = (et % LPR) * 4, cg = col0 + c;
+            const bool vec = (p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+            if (cg < p.Cout) {
+                for (int r = et / LPR; r < GT_ROWS; r += (2 * GT_CONV) / LPR) {
+                    const int64_t nr = row0 + r;
+                    if (nr >= p.N) break;
+                    const float4 v = *reinterpret_cast<const float4*>(stg + r * SLD + c);
+                    float* o;
+                    if (p.out_mode == 0) {
+                        o = p.out + (size_t)nr * p.out_ld + cg;
+                    } else {
+                        const int64_t per = (int64_t)p.dIH * p.dIW;
+                        const int64_t b = nr / per;
+                        const int rr = (int)(nr % per);
+                        const int iy = rr / p.dIW, ix = rr % p.dIW;
+                        const int sub = cg / p.dC, co = cg - sub * p.dC;
+                        const int dy = sub / p.ds, dx = sub - dy * p.ds;
+                        const size_t opix = ((size_t)b * p.dIH * p.ds + (size_t)iy * p.ds + dy) * (p.dIW * p.ds) +
+                                            (size_t)ix * p.ds + dx;
+                        o = p.out + opix * p.out_ld + co;
+                    }
+                    if (vec && cg + 3 < p.Cout) {
+                        *reinterpret_cast<float4*>(o) = v;
+                    } else {
+                        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (cg + j < p.Cout) o[j] = e[j];
                     }
                 }
             }

@@ -8,6 +8,9 @@
 
 No device->host synchronisation happens inside forward(): the voxel count stays on
 the device (the reference syncs at :106 and once per frame inside the op).
+The dense part (20 launches of 20-60 us each at one KITTI frame) is launch-bound from
+Python, so it is captured once per canvas shape into a CUDA graph and replayed
+(`use_graph=False` or O3DML_PP_GRAPH=0 keeps the eager launches).
 Built from a reference ``state_dict``; returns (cls, reg, dir) in NCHW like the
 reference head.
 """
@@ -30,8 +33,11 @@ class PointPillarsB200:
     """cfg keys: point_cloud_range, voxel_size, max_num_points, max_voxels (eval value),
     output_shape [ny, nx], layer_nums, layer_strides, upsample_strides."""
 
-    def __init__(self, state_dict, cfg, device=None):
+    def __init__(self, state_dict, cfg, device=None, use_graph=None):
         L.require_cuda()
+        import os
+        self.use_graph = (os.environ.get("O3DML_PP_GRAPH", "1") != "0") if use_graph is None else bool(use_graph)
+        self._graphs = {}
         self.device = dev = torch.device(device or "cuda")
         self.cfg = cfg
         sd = {k: v.detach().to("cpu", torch.float32) if v.is_floating_point() else v.cpu()
@@ -143,6 +149,27 @@ class PointPillarsB200:
         return out, OH, OW
 
     def backbone_neck_head(self, canvas):
+        """SECOND + SECONDFPN + Anchor3DHead on the NHWC canvas -> (cls, reg, dir) in NCHW."""
+        if not self.use_graph:
+            return self._bnh_eager(canvas)
+        key = (canvas.data_ptr(), tuple(canvas.shape))
+        ent = self._graphs.get(key)
+        if ent is None:
+            # eager pass first: sizes the cached buffers and runs the one-time cudaFuncSetAttribute
+            # calls, neither of which may happen under stream capture
+            self._bnh_eager(canvas)
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = L.lib().o3dml_launch_count()
+            with torch.cuda.graph(graph):
+                outs = self._bnh_eager(canvas)
+            ent = self._graphs[key] = (graph, outs, L.lib().o3dml_launch_count() - n0)
+        graph, outs, launches = ent
+        graph.replay()
+        L.lib().o3dml_launch_count_add(launches)
+        return tuple(o.clone() for o in outs)   # the graph's own outputs are overwritten by the next replay
+
+    def _bnh_eager(self, canvas):
         B, H, W = canvas.shape[0], canvas.shape[1], canvas.shape[2]
         x = canvas
         feats = []

@@ -9,6 +9,7 @@ import torch.nn.functional as F
 from open3d_ml_b200 import _lib as L
 
 L.TC_MIN_K = 8      # the tests exercise the tensor-core kernel on every aligned shape
+L.USE_ROW_MLP = False   # ... and not the row-per-thread kernel (it has its own tests below)
 from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
@@ -174,3 +175,54 @@ def test_linear_tc_is_magnitude_independent(mag):
     out = torch.empty(n, cout).cuda()
     L.linear([L.make_src(x)], L.pack_linear(w), out, act=None)
     assert rel_err(out, x.double() @ w.double()) < 2e-6
+
+
+ROW_SHAPES = [(3, 0, 8), (8, 0, 8), (16, 0, 8), (16, 0, 16), (16, 8, 32), (32, 0, 32), (64, 0, 32), (64, 0, 64),
+              (32, 32, 32), (32, 0, 64), (32, 0, 19)]
+
+
+@pytest.mark.parametrize("c0,c1,co", ROW_SHAPES)
+@pytest.mark.parametrize("n", [1, 257, 40000])
+def test_linear_rows_small(c0, c1, co, n, monkeypatch):
+    """rowmlp.cu (weights in the kernel parameter block, thread per row) vs float64 torch; the
+    second source is gathered through a batch-relative index as in the RandLA-Net decoder."""
+    monkeypatch.setattr(L, "USE_ROW_MLP", True)
+    assert L.lib().o3dml_linear_rows_small_supported(c0, c1, co) == 1
+    B = 2 if n > 1 else 1
+    a = rnd(B * n, c0, seed=1)
+    w = rnd(c0 + c1, co, seed=2) / (c0 + c1) ** 0.5
+    s, t = rnd(co, seed=3).abs() + 0.5, rnd(co, seed=4)
+    srcs, cols = [L.make_src(a)], [a.double()]
+    if c1:
+        nco = max(1, n // 3)
+        coarse = rnd(B * nco, c1, seed=5)
+        idx = torch.randint(0, nco, (B, n, 1), generator=torch.Generator().manual_seed(6)).cuda()
+        srcs.append(L.make_src(coarse, index=idx.view(-1), out_rows_per_batch=n, src_rows_per_batch=nco))
+        cols.append(torch.gather(coarse.view(B, nco, c1), 1, idx.expand(-1, -1, c1)).reshape(B * n, c1).double())
+    pw = L.pack_linear(w)
+    n0 = L.lib().o3dml_launch_count()
+    out = torch.full((B * n, co), float("nan")).cuda()
+    L.linear(srcs, pw, out, s, t, act="leaky", slope=0.2)
+    assert L.lib().o3dml_launch_count() == n0 + 1
+    ref = F.leaky_relu((torch.cat(cols, 1) @ w.double()) * s + t, 0.2)
+    assert rel_err(out, ref) < TOL
+    out2 = torch.full((B * n, co), float("nan")).cuda()
+    L.linear(srcs, pw, out2, None, t, act=None)
+    assert rel_err(out2, torch.cat(cols, 1) @ w.double() + t) < TOL
+
+
+def test_linear_rows_small_rejects_unsupported_shape_and_device_weights():
+    x = rnd(100, 24, seed=1)
+    arr = (L.Src * 1)(L.make_src(x))
+    out = torch.empty(100, 8).cuda()
+    w = torch.zeros(24, 8)
+    assert L.lib().o3dml_linear_rows_small_supported(24, 0, 8) == 0
+    rc = L.lib().o3dml_linear_rows_small(100, arr, 1, w.data_ptr(), None, None, 0, 0.0, L.ptr(out), 8, 8, L.stream())
+    assert rc != 0
+    x8 = rnd(100, 8, seed=2)
+    arr = (L.Src * 1)(L.make_src(x8))
+    rc = L.lib().o3dml_linear_rows_small(100, arr, 1, torch.zeros(8, 8).cuda().data_ptr(), None, None, 0, 0.0,
+                                         L.ptr(out), 8, 8, L.stream())
+    assert rc != 0
+    with pytest.raises(RuntimeError):
+        L.check(rc)

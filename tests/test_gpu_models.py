@@ -118,6 +118,27 @@ def test_pointpillars_waymo_shape_vs_port():
         assert o.shape == r.shape and rel_err(o, r) < TOL
 
 
+def test_pointpillars_graph_replay_equals_eager_launches():
+    """The dense part is replayed from a CUDA graph by default: same bits as the eager launches,
+    and results of consecutive calls do not alias."""
+    g = H.golden("pointpillars_small.npz")
+    sd, extra = H.state_dict("pointpillars_kitti.manifest.json", g["weight_seed"])
+    cfg = dict(extra["cfg"], point_cloud_range=[0, -10.24, -3, 20.48, 10.24, 1], output_shape=[128, 128])
+    fa = [torch.from_numpy(synth.lidar_frame(6000, 3, tuple(cfg["point_cloud_range"])))]
+    fb = [torch.from_numpy(synth.lidar_frame(5000, 4, tuple(cfg["point_cloud_range"])))]
+    eager = M.PointPillarsB200(sd, cfg, use_graph=False)
+    graph = M.PointPillarsB200(sd, cfg, use_graph=True)
+    ea, eb = eager(fa), eager(fb)
+    ga = graph(fa)          # capture + first replay
+    gb = graph(fb)          # replay on new data
+    ga2 = graph(fa)
+    for x, y, z, w in zip(ea, eb, ga, gb):
+        assert torch.equal(x, z) and torch.equal(y, w)
+    for x, z in zip(ea, ga2):
+        assert torch.equal(x, z)
+    assert not torch.equal(ga[0], gb[0])
+
+
 # --------------------------------------------------------------------- KPConv
 def test_kpfcnn_vs_golden_reference():
     g = H.golden("kpconv_small.npz")
