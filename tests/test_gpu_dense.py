@@ -148,7 +148,7 @@ def test_gather_max_batched_and_shadow():
     assert torch.equal(out2, ref2) and float(out2[0].abs().max()) == 0
 
 
-@pytest.mark.parametrize("cin,H", [(5, 27), (32, 35), (64, 40), (200, 7)])
+@pytest.mark.parametrize("cin,H", [(5, 27), (32, 35), (64, 40), (200, 7), (128, 33), (256, 20), (32, 3), (10, 9)])
 def test_kpconv_gather_vs_torch(cin, H):
     from oracle import models_torch as MT
     nq, ns, K = 333, 500, 15
