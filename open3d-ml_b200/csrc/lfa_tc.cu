@@ -58,6 +58,7 @@ struct LtcCfg {
     static constexpr bool TRANS = !STREAM && D >= 64;
     static constexpr int NTH = (TRANS && D == 128) ? 512 : 256;   // threads per CTA
     static constexpr int NPART = NTH / LTC_ROWS;                  // threads sharing one row
+    static constexpr int MINB = (TRANS && D == 64) ? 2 : 1;       // two CTAs per SM must fit the register file
     static constexpr int A_BYTES = D / 8 * LTC_ROWS * 16;  // one of hi / lo
     static constexpr int B_BYTES = STREAM ? 0 : TRANS ? D / 8 * LTC_ROWS * 16 : D / 8 * D * 16;
     static constexpr int I_BYTES = TRANS ? D / 8 * LTC_ROWS * 16 : 0;   // identity operand (hi only)
@@ -173,7 +174,7 @@ __device__ __forceinline__ void gemm_streamed(uint32_t tmem_d, const uint8_t* a_
 }
 
 template <int D, int STAGE>
-__global__ void __launch_bounds__((LtcCfg<D, STAGE>::NTH), 1)
+__global__ void __launch_bounds__((LtcCfg<D, STAGE>::NTH), (LtcCfg<D, STAGE>::MINB))
 lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
     using C = LtcCfg<D, STAGE>;
     constexpr int H = C::H, NTH = C::NTH, NPART = C::NPART;
@@ -259,14 +260,74 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
     uint32_t ph_main[2] = {0, 0};  // parities of mbar[0] (lse2) and mbar[1] (scores)
     uint32_t ph_ring[2] = {0, 0};  // parities of mbar[2], mbar[3] (weight ring)
 
+    // TRANS kernels software-pipeline the gathers over tiles: the neighbour index of tile t+2 and the
+    // coordinates / feature rows of tile t+1 are requested at the top of tile t and land while its
+    // MMAs and epilogue run (two dependent global round trips leave the per-tile critical path).
+    constexpr bool PREF = C::TRANS;
+    constexpr int FCH = PREF ? (H / 8) / NPART : 1;      // feature chunks (8 channels) per thread
+    int64_t g_nx = p.total, nb_nx = -1, g_n2 = p.total, nb_n2 = -1;
+    float qc_nx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float4 f_nx[FCH][2];
+    auto load_idx = [&](int64_t t, int64_t& g_, int64_t& nb_) {
+        g_ = p.total;
+        nb_ = -1;
+        if (t < p.num_tiles) {
+            g_ = t * (LTC_ROWS / LTC_K) + (row >> 4);
+            if (g_ < p.total)
+                nb_ = (g_ / p.n_per_batch) * p.n_per_batch + load_index(p.nidx, g_ * LTC_K + (row & 15), p.nidx_is64);
+        }
+    };
+    auto load_data = [&](int64_t g_, int64_t nb_, float* qc, float4 (*f)[2]) {
+        if (nb_ >= 0) {
+            qc[0] = p.coords[3 * g_]; qc[1] = p.coords[3 * g_ + 1]; qc[2] = p.coords[3 * g_ + 2];
+            qc[3] = p.coords[3 * nb_]; qc[4] = p.coords[3 * nb_ + 1]; qc[5] = p.coords[3 * nb_ + 2];
+#pragma unroll
+            for (int i = 0; i < FCH; ++i) {
+                const float* src = p.feat + (size_t)nb_ * H + (half + i * NPART) * 8;
+                f[i][0] = *reinterpret_cast<const float4*>(src);
+                f[i][1] = *reinterpret_cast<const float4*>(src + 4);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) qc[i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < FCH; ++i) f[i][0] = f[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    if (PREF) {
+        load_idx(blockIdx.x, g_nx, nb_nx);
+        load_data(g_nx, nb_nx, qc_nx, f_nx);
+        load_idx((int64_t)blockIdx.x + gridDim.x, g_n2, nb_n2);
+    }
+
     for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         // ---------------- neighbour id + 10-channel encoding of this thread's row
-        const int64_t g = tile * (LTC_ROWS / LTC_K) + (row >> 4);
+        int64_t g = tile * (LTC_ROWS / LTC_K) + (row >> 4);
         int64_t nb = -1;
         float e[10];
+        float4 f_cur[FCH][2];
 #pragma unroll
         for (int q = 0; q < 10; ++q) e[q] = 0.f;
-        if (g < p.total) {
+        if (PREF) {
+            g = g_nx;
+            nb = nb_nx;
+            float qc[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) qc[i] = qc_nx[i];
+#pragma unroll
+            for (int i = 0; i < FCH; ++i) { f_cur[i][0] = f_nx[i][0]; f_cur[i][1] = f_nx[i][1]; }
+            g_nx = g_n2;
+            nb_nx = nb_n2;
+            load_data(g_nx, nb_nx, qc_nx, f_nx);                       // tile t+1: in flight from here
+            load_idx(tile + 2 * (int64_t)gridDim.x, g_n2, nb_n2);      // tile t+2: index
+            if (nb >= 0) {
+                const float dx = qc[0] - qc[3], dy = qc[1] - qc[4], dz = qc[2] - qc[5];
+                e[0] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+                e[1] = dx; e[2] = dy; e[3] = dz;
+                e[4] = qc[0]; e[5] = qc[1]; e[6] = qc[2];
+                e[7] = qc[3]; e[8] = qc[4]; e[9] = qc[5];
+            }
+        } else if (g < p.total) {
             const int64_t b = g / p.n_per_batch;
             nb = b * p.n_per_batch + load_index(p.nidx, g * LTC_K + (row & 15), p.nidx_is64);
             const float qx = p.coords[3 * g], qy = p.coords[3 * g + 1], qz = p.coords[3 * g + 2];
@@ -357,9 +418,13 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
         }
         // ---------------- gathered neighbour features -> channels [0, H)  (overwrites r1 in stage 2:
         // the lse2 MMAs that read it have completed)
-        for (int ch = half; ch < H / 8; ch += NPART) {
+        for (int ch = half, fi = 0; ch < H / 8; ch += NPART, ++fi) {
             float x[8];
-            if (nb >= 0) {
+            if (PREF) {
+                const float4 v0 = f_cur[fi < FCH ? fi : 0][0], v1 = f_cur[fi < FCH ? fi : 0][1];
+                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+            } else if (nb >= 0) {
                 const float4 v0 = *reinterpret_cast<const float4*>(p.feat + (size_t)nb * H + ch * 8);
                 const float4 v1 = *reinterpret_cast<const float4*>(p.feat + (size_t)nb * H + ch * 8 + 4);
                 x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
