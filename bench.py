@@ -470,9 +470,14 @@ def run_b200(args, wl):
             e[2] += wl.roofline_bytes(d, n)
             e[3] += wl.roofline_flops(d, s, n)
         ach = tot_bytes / (tot_ms * 1e-3) / 1e9
-        roof = dict(bound="hbm", kernel="lfa_pool: tcgen05 lfa_pool_tc_kernel (d>=32) + lfa16_kernel (d=16), all 8 launches per step",
+        # DRAM bytes (read + write) of the 8 launches of one step, from the committed ncu --set full capture
+        # (profiles/r01_lfa_ncu_full.md); only valid for the configuration that capture was taken on
+        traffic = 209.2e6 if (wl.B, wl.N) == (8, 45056) else None
+        roof = dict(bound="hbm", kernel="lfa_pool: tcgen05 lfa_pool_tc_kernel (d>=64) + lfa16c_kernel (d=16), all 8 launches per step",
                     achieved=round(ach, 2), peak=pk["hbm_gbs"], unit="GB/s", frac=round(ach / pk["hbm_gbs"], 5),
-                    traffic=None, peak_source=pk["src"],
+                    algorithmic_bytes=int(tot_bytes / max(1, args.steps)), traffic=traffic,
+                    traffic_source="profiles/r01_lfa_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum, per step)",
+                    peak_source=pk["src"],
                     share_of_step=round(tot_ms / ms, 4),
                     fp32_tflops=round(tot_flops / (tot_ms * 1e-3) / 1e12, 3),
                     per_kernel={k: dict(avg_us=round(1e3 * e[0] / e[1], 2),
