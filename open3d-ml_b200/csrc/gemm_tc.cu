@@ -114,9 +114,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 template <int BN>
 struct GtCfg {
-    // chunk stride of the A operand padded by 16 B (UMMA LBO is free): lanes that differ in the chunk
-    // index hit different banks when they convert their slots in place
-    static constexpr int A_LBO = GT_ROWS * 16 + 16;
+    // chunk stride of the A operand padded by 32 B (UMMA LBO is free).  A quarter-warp of the loaders /
+    // converters touches (row m, chunk c) for m in {m0, m0+1}, c in 0..3: bank = 8c + 4(m - m0) mod 32 is then
+    // distinct for all eight 16-byte accesses (a 16 B pad made (c, m0+1) collide with (c+1, m0))
+    static constexpr int A_LBO = GT_ROWS * 16 + 32;
     static constexpr int A_BYTES = GT_CH * A_LBO;         // one of hi/lo per stage
     static constexpr int B_BYTES = GT_CH * BN * 16;
     static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
