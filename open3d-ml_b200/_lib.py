@@ -146,14 +146,20 @@ class PackedWeight:
         self._host_affine = {}
 
     def host_affine(self, scale, shift):
-        """Host copies of the folded-BN scale / shift of this layer (made once, at first use)."""
-        key = (0 if scale is None else scale.data_ptr(), 0 if shift is None else shift.data_ptr())
+        """Host copies of the folded-BN scale / shift of this layer (made once, at first use).  The cache
+        entry keeps the device tensors alive (so their addresses cannot be reused by other tensors) and is
+        keyed by their version counters (an in-place update invalidates it)."""
+        def k(t):
+            return (0, 0) if t is None else (t.data_ptr(), t._version)
+        key = (k(scale), k(shift))
         ent = self._host_affine.get(key)
         if ent is None:
             ent = (None if scale is None else scale.detach().float().cpu().contiguous(),
-                   None if shift is None else shift.detach().float().cpu().contiguous())
+                   None if shift is None else shift.detach().float().cpu().contiguous(), scale, shift)
+            if len(self._host_affine) > 8:      # a layer has one (scale, shift) pair; do not grow without bound
+                self._host_affine.clear()
             self._host_affine[key] = ent
-        return ent
+        return ent[0], ent[1]
 
     @property
     def shape(self):

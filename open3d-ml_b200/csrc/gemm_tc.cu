@@ -5,8 +5,8 @@
 //   * A k-slices (32 channels) are converted by the CTA to fp16 hi/lo pairs and written straight into
 //     the UMMA chunk-major shared-memory layout (tc.cuh), 3 MMAs per k-step (3xFP16, ~2^-21 relative),
 //   * B comes from a host-packed hi/lo operand image ([K/8][Cout_pad][8 halves], zero padded),
-//   * the accumulator [128 x BN] lives in TMEM; a 3-stage ring lets the conversion of slice s+1
-//     overlap the MMAs of slice s (global loads of slice s+1 are in flight across the barrier).
+//   * the accumulator [128 x BN] lives in TMEM (two column ranges, chunked accumulation, see "flush"
+//     below); a GT_STAGES-deep ring of (A, B) slices decouples the loader, converter and MMA warps.
 // fp16 has a narrow exponent range (the lo parts go subnormal for |x| < 0.125 and precision
 // decays to 1e-4 for |x| ~ 1e-4), so every CTA first takes the max |A| of its own tile (one extra
 // pass over data that is read again right after, i.e. L2 hits) and rescales by an exact power of two
@@ -127,17 +127,21 @@ struct GtCfg {
 };
 
 // Pipeline (per CTA, one [128 x BN] output tile, k-slices of 32 channels through a GT_STAGES ring),
-// 12 warps with fixed roles -- the roles are kept in different threads on purpose: the proxy fence that
+// 13 warps with fixed roles -- the roles are kept in different threads on purpose: the proxy fence that
 // publishes converted operands drains the issuing thread's outstanding memory operations, so a thread
 // that prefetches AND fences never has a load in flight (measured 2.5 us per slice at any depth), and a
 // thread that converts AND issues MMAs serialises 700 + 740 cycles per slice:
-//   warp 0        MMA issuer: waits conv[stage], one elected lane issues 6 tcgen05.mma (descriptors stay
-//                 in uniform registers), tcgen05.commit -> empty[stage] (+ chunk[] at chunk ends)
-//   warps 1-4     loaders: cp.async raw fp32 A pieces straight INTO the slots where their fp16 hi / lo
-//                 words will live + the weight-image slices; cp.async.mbarrier.arrive -> full[stage]
+//   warp 0        MMA issuer: hands the weight-image slices to the bulk-copy engine (cp.async.bulk,
+//                 bytes counted on full[stage]), waits conv[stage], one elected lane issues 6 tcgen05.mma,
+//                 tcgen05.commit -> empty[stage] (+ chunk[] at chunk ends)
+//   warps 1-4     loaders: raw fp32 A pieces global -> registers -> shared (LDG.128 / STS.128, two slices
+//                 in flight) straight INTO the slots where their fp16 hi / lo words will live;
+//                 mbarrier.arrive -> full[stage]
 //   warps 5-8 /   two converter groups taking alternate slices: each thread rewrites its own 16-byte
 //   warps 9-12    slots in place (x * 2^e -> hi, lo), fences, arrives on conv[stage]; group g also owns
-//                 column half g of the accumulator for the flushes and the epilogue
+//                 column half g of the accumulator for the flushes and the epilogue; the same 8 warps
+//                 run the range pass (max |A| of the tile) on their own named barrier at the start and
+//                 the shared-memory-staged, row-coalesced output stores at the end
 //   flush         every GT_FLUSH slices the TMEM accumulator is added (RN) into registers and the next
 //                 chunk starts fresh in the other TMEM buffer: the tensor core accumulates with
 //                 truncation (measured -3e-8 relative per accumulation, -5e-5 at K = 7680 otherwise)
@@ -390,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             }
         }
     } else if (warp < 5) {
-        // ================================================================= loaders (128 threads)
+        // ================================================================= loaders (GT_LOADERS threads)
         const int rt = tid - 32;
         constexpr int LA = (GT_ROWS * GT_CH) / GT_LOADERS;                    // (row, chunk) items per thread
         // everything that does not depend on the slice index is resolved once
