@@ -87,3 +87,21 @@ def test_shim_exposes_the_reference_tree_unmodified():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "ok 1242307" in r.stdout
+
+
+def test_pipelined_runner_tree_helpers_and_cpu_refusal():
+    """The pytree helpers of pipeline.py on CPU tensors, and the runner's refusal to exist without CUDA."""
+    import torch
+    from open3d_ml_b200 import pipeline as P
+    host = dict(a=[torch.arange(6.).view(2, 3), torch.ones(4, dtype=torch.int64)], b=torch.zeros(2), n=7, z=None)
+    dev = P._alloc_like(host, "cpu")
+    assert P._same_layout(dev, host) and dev["n"] == 7 and dev["z"] is None
+    assert dev["a"][0].shape == (2, 3) and dev["a"][1].dtype == torch.int64
+    out = P._copy_tree(dev, host)
+    assert torch.equal(out["a"][0], host["a"][0]) and torch.equal(out["a"][1], host["a"][1]) and out["n"] == 7
+    other = dict(host, b=torch.zeros(3))
+    assert not P._same_layout(dev, other)
+    assert not P._same_layout(dev, dict(a=host["a"], b=host["b"], n=7))          # key set differs
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            P.PipelinedRunner(lambda x: x)
