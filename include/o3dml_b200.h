@@ -195,8 +195,8 @@ O3DML_API int o3dml_deconv_nhwc_tc(const float* in, int batch, int H, int W, int
  * HBM-bound and need neither shared memory nor barriers. */
 O3DML_API int o3dml_linear_rows_small_supported(int channels0, int channels1, int out_channels);
 O3DML_API int o3dml_linear_rows_small(int64_t num_rows, const o3dml_src_t* srcs, int num_srcs,
-                                      const float* host_weight_t, const float* host_scale,
-                                      const float* host_shift, int act, float slope, float* out, int out_ld,
+                                      const float* h_weight_t, const float* h_scale,
+                                      const float* h_shift, int act, float slope, float* out, int out_ld,
                                       int out_channels, void* stream);
 
 /* ---------------------------------------------------------- RandLA-Net ---- */
@@ -220,7 +220,7 @@ O3DML_API int o3dml_randla_lfa_pool(int stage, int d, const float* coords, const
 #define O3DML_LFA16_WEIGHT_FLOATS 448
 O3DML_API int o3dml_randla_lfa16_pool(int stage, const float* coords, const void* neighbor_idx, int idx_is64,
                                       int num_neighbors, const float* feat, int64_t batch,
-                                      int64_t n_per_batch, const float* host_weights, float* agg,
+                                      int64_t n_per_batch, const float* h_weights, float* agg,
                                       void* stream);
 
 /* Tensor-core (tcgen05, 3xFP16 split) variant of o3dml_randla_lfa_pool, same contract, d in

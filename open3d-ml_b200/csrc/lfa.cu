@@ -607,15 +607,15 @@ extern "C" int o3dml_randla_lfa_pool(int stage, int d, const float* coords, cons
 
 extern "C" int o3dml_randla_lfa16_pool(int stage, const float* coords, const void* neighbor_idx, int idx_is64,
                                        int num_neighbors, const float* feat, int64_t batch,
-                                       int64_t n_per_batch, const float* host_weights, float* agg,
+                                       int64_t n_per_batch, const float* h_weights, float* agg,
                                        void* stream) {
     O3DML_CHECK(stage == 1 || stage == 2, "lfa16: stage must be 1 or 2");
     O3DML_CHECK(num_neighbors == LFA_K, "lfa16: the fused kernel is built for 16 neighbours");
     O3DML_CHECK(batch * n_per_batch < ((int64_t)1 << 31), "lfa16: too many points");
-    O3DML_CHECK(host_weights != nullptr, "lfa16: host_weights is null");
+    O3DML_CHECK(h_weights != nullptr, "lfa16: h_weights is null");
     cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, host_weights) == cudaSuccess)
-        O3DML_CHECK(attr.type != cudaMemoryTypeDevice, "lfa16: host_weights must point to HOST memory");
+    if (cudaPointerGetAttributes(&attr, h_weights) == cudaSuccess)
+        O3DML_CHECK(attr.type != cudaMemoryTypeDevice, "lfa16: h_weights must point to HOST memory");
     else
         cudaGetLastError();
     LfaParams p;
@@ -625,7 +625,7 @@ extern "C" int o3dml_randla_lfa16_pool(int stage, const float* coords, const voi
     p.agg = agg;
     if (p.total == 0) return O3DML_OK;
     Lfa16W w;
-    memcpy(w.v, host_weights, sizeof(w.v));
+    memcpy(w.v, h_weights, sizeof(w.v));
     cudaStream_t st = (cudaStream_t)stream;
     return stage == 1 ? lfa16c_launch<1>(p, w, st) : lfa16c_launch<2>(p, w, st);
 }

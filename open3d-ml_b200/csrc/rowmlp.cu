@@ -155,13 +155,13 @@ extern "C" int o3dml_linear_rows_small_supported(int c0, int c1, int out_channel
 }
 
 extern "C" int o3dml_linear_rows_small(int64_t num_rows, const o3dml_src_t* srcs, int num_srcs,
-                                       const float* host_weight_t, const float* host_scale,
-                                       const float* host_shift, int act, float slope, float* out, int out_ld,
+                                       const float* h_weight_t, const float* h_scale,
+                                       const float* h_shift, int act, float slope, float* out, int out_ld,
                                        int out_channels, void* stream) {
     O3DML_CHECK(num_rows >= 0 && srcs && (num_srcs == 1 || num_srcs == 2), "linear_rows_small: bad arguments");
-    O3DML_CHECK(host_weight_t && out, "linear_rows_small: null weight / output");
+    O3DML_CHECK(h_weight_t && out, "linear_rows_small: null weight / output");
     O3DML_CHECK(out_ld >= out_channels, "linear_rows_small: out_ld < out_channels");
-    for (const void* hp : {(const void*)host_weight_t, (const void*)host_scale, (const void*)host_shift}) {
+    for (const void* hp : {(const void*)h_weight_t, (const void*)h_scale, (const void*)h_shift}) {
         if (!hp) continue;
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, hp) == cudaSuccess)
@@ -174,7 +174,7 @@ extern "C" int o3dml_linear_rows_small(int64_t num_rows, const o3dml_src_t* srcs
     cudaStream_t st = (cudaStream_t)stream;
 #define RM_CASE(A, B, C)                                                                              \
     if (c0 == A && c1 == B && out_channels == C)                                                      \
-        return rowmlp_launch<A, B, C>(num_rows, srcs, host_weight_t, host_scale, host_shift, act, slope, out, \
+        return rowmlp_launch<A, B, C>(num_rows, srcs, h_weight_t, h_scale, h_shift, act, slope, out, \
                                       out_ld, st);
 #include "rowmlp_shapes.inc"
 #undef RM_CASE
