@@ -222,8 +222,8 @@ def linear(srcs, weight, out, scale=None, shift=None, residual=None, act=None, s
     return out
 
 
-def pack_operand_image(w_nk):
-    """fp32 [N, K] (K contiguous, i.e. nn.Linear's [out, in]) -> uint8 CUDA tensor holding the
+def pack_operand_image_host(w_nk):
+    """fp32 [N, K] (K contiguous, i.e. nn.Linear's [out, in]) -> uint8 CPU tensor holding the
     3xFP16 operand images of csrc/tc.cuh: [K/8][N][8 halves] of hi = fp16(w), then the same
     layout of lo = fp16(w - hi)."""
     w = w_nk.detach().to(torch.float32).cpu().clamp(-65504.0, 65504.0)
@@ -234,4 +234,9 @@ def pack_operand_image(w_nk):
 
     def img(h):
         return h.view(n, k // 8, 8).permute(1, 0, 2).contiguous().view(-1)
-    return torch.cat([img(hi), img(lo)]).view(torch.uint8).cuda()
+    return torch.cat([img(hi), img(lo)]).view(torch.uint8)
+
+
+def pack_operand_image(w_nk):
+    """pack_operand_image_host, moved to the device."""
+    return pack_operand_image_host(w_nk).cuda()
