@@ -8,8 +8,6 @@ import torch.nn.functional as F
 
 from open3d_ml_b200 import _lib as L
 
-L.TC_MIN_K = 8      # the tests exercise the tensor-core kernel on every aligned shape
-L.USE_ROW_MLP = False   # ... and not the row-per-thread kernel (it has its own tests below)
 from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
@@ -21,6 +19,15 @@ def _no_tf32():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     yield
+
+
+@pytest.fixture(autouse=True)
+def _kernel_routing(monkeypatch):
+    """In this module the tensor-core kernel takes every aligned shape (the product routes K < 128 to
+    the SIMT / row-per-thread kernels) and the row-per-thread kernel is off except in its own tests;
+    restored afterwards so that the model tests see the product's routing."""
+    monkeypatch.setattr(L, "TC_MIN_K", 8)
+    monkeypatch.setattr(L, "USE_ROW_MLP", False)
 
 
 def rnd(*shape, seed=0):
