@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define O3DML_ABI_VERSION 1
+#define O3DML_ABI_VERSION 2
 #define O3DML_API __attribute__((visibility("default")))
 
 /* activation codes */
@@ -163,25 +163,27 @@ O3DML_API int o3dml_deconv_nhwc(const float* in, int batch, int H, int W, int C,
                       const float* weight_t, const float* scale, const float* shift, int act,
                       float slope, float* out, int out_ld, int out_channels, void* stream);
 
-/* Tensor-core (tcgen05, 3xFP16 split) variants of the three dense entry points above.  Instead of
- * weight_t they take the host-packed fp16 hi/lo operand image of the weight [n_pad][k_pad]
- * (zero padded; k_pad % 32 == 0; n_pad in {32, 64, 128*j}; open3d_ml_b200._lib.pack_linear), holding
- * weight * 2^weight_exp (power-of-two range normalisation, undone in the epilogue together with the
- * per-CTA normalisation of the gathered A tile).  Every source needs a multiple of 8 channels. */
+/* Tensor-core (tcgen05, kind::tf32, 3xTF32 split: ~2^-21 relative per product) variants of the three
+ * dense entry points above.  Instead of weight_t they take the host-packed TF32 hi/lo image of the
+ * weight: fp32 [2 * n_pad][k_pad] row-major, rows [0, n_pad) = tf32(w[:, n]) and rows [n_pad, 2 n_pad) =
+ * tf32(w - hi) (zero padded; k_pad % 32 == 0; n_pad in {32, 64, 128*j}; 16-byte aligned;
+ * open3d_ml_b200._lib.pack_linear).  Identity sources and convolution taps are fetched with
+ * cp.async.bulk.tensor (the library encodes the tensor maps per call), gathered sources with cp.async.
+ * Contract on the sources (o3dml_linear_tc_supported returns 1 when it holds): channels % 4 == 0,
+ * ld % 4 == 0, 16-byte aligned data, and channels % 32 == 0 for every source but the last;
+ * o3dml_conv3x3_nhwc_tc needs C % 32 == 0. */
+O3DML_API int o3dml_linear_tc_supported(const o3dml_src_t* srcs, int num_srcs);
 O3DML_API int o3dml_linear_tc(int64_t num_rows, const o3dml_src_t* srcs, int num_srcs,
-                              const void* weight_image, int k_pad, int n_pad, int weight_exp,
-                              const float* scale,
+                              const void* weight_image, int k_pad, int n_pad, const float* scale,
                               const float* shift, const float* residual, int residual_ld, int act,
                               float slope, float* out, int out_ld, int out_channels,
                               int out_nchw_plane, void* stream);
 O3DML_API int o3dml_conv3x3_nhwc_tc(const float* in, int batch, int H, int W, int C, int stride,
-                                    const void* weight_image, int k_pad, int n_pad, int weight_exp,
-                              const float* scale,
+                                    const void* weight_image, int k_pad, int n_pad, const float* scale,
                                     const float* shift, int act, float slope, float* out,
                                     int out_channels, void* stream);
 O3DML_API int o3dml_deconv_nhwc_tc(const float* in, int batch, int H, int W, int C, int stride,
-                                   const void* weight_image, int k_pad, int n_pad, int weight_exp,
-                              const float* scale,
+                                   const void* weight_image, int k_pad, int n_pad, const float* scale,
                                    const float* shift, int act, float slope, float* out, int out_ld,
                                    int out_channels, void* stream);
 

@@ -12,6 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libo3dml_b200.so")
 _lib = None
+ABI_VERSION = 2
 
 c_void_p, c_int, c_int64, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                ctypes.c_float, ctypes.c_size_t)
@@ -44,9 +45,10 @@ _SIGNATURES = {
     "o3dml_linear": (I, [L, ctypes.POINTER(Src), I, P, P, P, P, I, I, F, P, I, I, I, P]),
     "o3dml_conv3x3_nhwc": (I, [P, I, I, I, I, I, P, P, P, I, F, P, I, P]),
     "o3dml_deconv_nhwc": (I, [P, I, I, I, I, I, P, P, P, I, F, P, I, I, P]),
-    "o3dml_linear_tc": (I, [L, ctypes.POINTER(Src), I, P, I, I, I, P, P, P, I, I, F, P, I, I, I, P]),
-    "o3dml_conv3x3_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, I, P, P, I, F, P, I, P]),
-    "o3dml_deconv_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, I, P, P, I, F, P, I, I, P]),
+    "o3dml_linear_tc_supported": (I, [ctypes.POINTER(Src), I]),
+    "o3dml_linear_tc": (I, [L, ctypes.POINTER(Src), I, P, I, I, P, P, P, I, I, F, P, I, I, I, P]),
+    "o3dml_conv3x3_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, P, P, I, F, P, I, P]),
+    "o3dml_deconv_nhwc_tc": (I, [P, I, I, I, I, I, P, I, I, P, P, I, F, P, I, I, P]),
     "o3dml_randla_lfa_pool": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
     "o3dml_linear_rows_small_supported": (I, [I, I, I]),
     "o3dml_linear_rows_small": (I, [L, P, I, P, P, P, I, F, P, I, I, P]),
@@ -76,7 +78,7 @@ def lib():
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(h, name)
             fn.restype, fn.argtypes = res, args
-        if h.o3dml_abi_version() != 1:
+        if h.o3dml_abi_version() != ABI_VERSION:
             raise RuntimeError("open3d_ml_b200: ABI version mismatch")
         _lib = h
     return _lib
@@ -125,9 +127,26 @@ def make_src(data, index=None, index_ld=1, out_rows_per_batch=0, src_rows_per_ba
 USE_TC_GEMM = os.environ.get("O3DML_GEMM_TC", "1") != "0"
 
 
+def tf32_round(x):
+    """fp32 -> nearest TF32 (10 explicit mantissa bits, ties to even), returned as fp32."""
+    u = x.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    u = (u + 0xFFF + ((u >> 13) & 1)) & 0xFFFFE000
+    u = torch.where(u >= 2 ** 31, u - 2 ** 32, u)
+    return u.to(torch.int32).view(torch.float32)
+
+
+def pack_tf32_image_host(w_nk):
+    """fp32 [N, K] (K contiguous) -> fp32 CPU tensor [2 * N, K]: rows [0, N) = hi = tf32(w),
+    rows [N, 2N) = lo = tf32(w - hi).  gemm_tc.cu fetches [BN x 32] boxes of it by TMA."""
+    w = w_nk.detach().to(torch.float32).cpu().contiguous()
+    hi = tf32_round(w)
+    lo = tf32_round(w - hi)
+    return torch.cat([hi, lo], 0).contiguous()
+
+
 class PackedWeight:
     """A dense-layer weight in both forms: fp32 [K, Cout] for the SIMT kernel (gemm.cu) and the
-    zero-padded fp16 hi/lo operand image for the tcgen05 kernel (gemm_tc.cu)."""
+    zero-padded TF32 hi/lo image [2 * n_pad, k_pad] for the tcgen05 kernel (gemm_tc.cu)."""
 
     def __init__(self, w_kc):
         w = w_kc.detach().to(torch.float32).cpu().contiguous()
@@ -135,13 +154,9 @@ class PackedWeight:
         self.wt = w.cuda()
         self.k_pad = (self.k + 31) // 32 * 32
         self.n_pad = 32 if self.cout <= 32 else 64 if self.cout <= 64 else (self.cout + 127) // 128 * 128
-        wmax = float(w.abs().max())
-        # power-of-two range normalisation: max |w| * 2^w_exp in [2^13, 2^14) keeps the fp16 lo parts normal
-        self.w_exp = int(13 - math.floor(math.log2(wmax))) if 0.0 < wmax < 3.0e38 else 0
-        self.w_exp = max(-100, min(100, self.w_exp))
         wp = torch.zeros((self.n_pad, self.k_pad), dtype=torch.float32)
-        wp[:self.cout, :self.k] = w.t() * (2.0 ** self.w_exp)
-        self.img = pack_operand_image(wp)
+        wp[:self.cout, :self.k] = w.t()
+        self.img = pack_tf32_image_host(wp).cuda()
         self.host = w                      # fp32 [K, Cout] on the host: rowmlp.cu takes it by value
         self._host_affine = {}
 
@@ -174,12 +189,14 @@ TC_MIN_K = int(os.environ.get("O3DML_GEMM_TC_MIN_K", "128"))
 
 
 def _tc_ok(srcs):
-    """Tensor-core kernel only where it pays: every source 8-channel aligned, and K >= 128 (below that the
-    per-CTA setup of the warp-specialised tcgen05 pipeline, one CTA per SM, costs more than the whole
-    SIMT tile: 188 vs ~40 us measured on the 360k-row K<=96 layers of RandLA-Net)."""
+    """Tensor-core kernel only where it pays (K >= TC_MIN_K) and where the operand contract of gemm_tc.cu
+    holds: every source 4-channel aligned with 16-byte aligned rows, and every source but the last a
+    multiple of 32 channels (a 32-channel k-slice never straddles two sources)."""
     if not USE_TC_GEMM or sum(s.channels for s in srcs) < TC_MIN_K:
         return False
-    return all((s.channels % 8 == 0) and (s.ld % 4 == 0) and (s.data % 16 == 0) for s in srcs)
+    if any(s.channels % 32 for s in srcs[:-1]):
+        return False
+    return all((s.channels % 4 == 0) and (s.ld % 4 == 0) and (s.data % 16 == 0) for s in srcs)
 
 
 USE_ROW_MLP = os.environ.get("O3DML_ROW_MLP", "1") != "0"
@@ -212,7 +229,7 @@ def linear(srcs, weight, out, scale=None, shift=None, residual=None, act=None, s
         check(lib().o3dml_linear_rows_small(n, arr, len(srcs), weight.host.data_ptr(), ptr(hs), ptr(ht),
                                             act_code(act), float(slope), ptr(out), ld, co, stream()))
     elif packed and _tc_ok(srcs):
-        check(lib().o3dml_linear_tc(n, arr, len(srcs), ptr(weight.img), weight.k_pad, weight.n_pad, weight.w_exp,
+        check(lib().o3dml_linear_tc(n, arr, len(srcs), ptr(weight.img), weight.k_pad, weight.n_pad,
                                     ptr(scale), ptr(shift), ptr(residual), res_ld, act_code(act),
                                     float(slope), ptr(out), ld, co, out_nchw_plane, stream()))
     else:

@@ -137,9 +137,9 @@ class PointPillarsB200:
         OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
         out = self._get(name, (B, OH, OW, cout))
         pw = self.w[name + ".wt"]
-        if L.USE_TC_GEMM and cin % 8 == 0:
+        if L.USE_TC_GEMM and cin % 32 == 0:
             L.check(L.lib().o3dml_conv3x3_nhwc_tc(L.ptr(x), B, H, W, cin, stride, L.ptr(pw.img), pw.k_pad,
-                                                  pw.n_pad, pw.w_exp, L.ptr(self.w[name + ".s"]),
+                                                  pw.n_pad, L.ptr(self.w[name + ".s"]),
                                                   L.ptr(self.w[name + ".t"]), 1, 0.0, L.ptr(out), cout,
                                                   L.stream()))
         else:
@@ -185,9 +185,9 @@ class PointPillarsB200:
             if h * us != OH or w_ * us != OW:
                 raise RuntimeError("PointPillarsB200: neck scales do not line up")
             pw = self.w[p + ".wt"]
-            if L.USE_TC_GEMM and cin % 8 == 0:
+            if L.USE_TC_GEMM and cin % 4 == 0:
                 L.check(L.lib().o3dml_deconv_nhwc_tc(L.ptr(f), B, h, w_, cin, us, L.ptr(pw.img), pw.k_pad,
-                                                     pw.n_pad, pw.w_exp, L.ptr(self.w[p + ".s"]), L.ptr(self.w[p + ".t"]),
+                                                     pw.n_pad, L.ptr(self.w[p + ".s"]), L.ptr(self.w[p + ".t"]),
                                                      1, 0.0, neck.data_ptr() + 4 * off, self.neck_channels,
                                                      co, L.stream()))
             else:

@@ -27,7 +27,7 @@ def test_library_builds_loads_and_exports_everything():
     for name in declared_symbols():
         assert hasattr(h, name), name
     assert set(_lib.EXPORTS) == set(declared_symbols())     # python binding covers the header
-    assert _lib.lib().o3dml_abi_version() == 1
+    assert _lib.lib().o3dml_abi_version() == _lib.ABI_VERSION == 2
     assert _lib.lib().o3dml_last_error() is not None
 
 

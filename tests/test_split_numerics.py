@@ -88,3 +88,43 @@ def test_packed_weight_exponent_matches_the_kernel_contract():
     lo = img[n_pad * k_pad:].view(k_pad // 8, n_pad, 8).permute(1, 0, 2).reshape(n_pad, k_pad).float()
     assert float(((hi + lo)[:40, :96] * 2.0 ** -e - w.t()).abs().max() / wmax) < 2.0 ** -21
     assert float((hi + lo)[40:].abs().max()) == 0.0                                # zero padding
+
+
+# ---- the 3xTF32 split of gemm_tc.cu (round 2) -------------------------------------------------------
+def _tf32_trunc(x):
+    return (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def test_tf32_split_three_products_reach_2e_minus_6():
+    """Emulates gemm_tc.cu: A: hi = x & 0xFFFFE000, lo = x - hi (the tensor core truncates lo to TF32);
+    W: host-side round-to-nearest split (_lib.pack_tf32_image_host); products accumulated in float64
+    here (the kernel's fp32 accumulation adds its own ~1e-7).  No range normalisation is needed: the
+    error does not depend on the magnitude of the operands."""
+    import torch
+    from open3d_ml_b200 import _lib as L
+    rng = np.random.default_rng(0)
+    for mag in (1e-20, 1e-6, 1.0, 3e4, 1e20):
+        a = (rng.standard_normal((64, 256)) * mag).astype(np.float32)
+        w = (rng.standard_normal((256, 32)) / 16).astype(np.float32)
+        img = L.pack_tf32_image_host(torch.from_numpy(np.ascontiguousarray(w.T))).numpy()
+        wh, wl = img[:32].T.astype(np.float64), img[32:].T.astype(np.float64)
+        assert np.array_equal(_tf32_trunc(img), img)                 # both images are TF32-exact
+        ah = _tf32_trunc(a)
+        al = _tf32_trunc(a - ah)                                     # exact subtraction, then HW truncation
+        ref = a.astype(np.float64) @ w.astype(np.float64)
+        got = ah.astype(np.float64) @ wh + ah.astype(np.float64) @ wl + al.astype(np.float64) @ wh
+        one = ah.astype(np.float64) @ wh
+        scale = np.abs(ref).max()
+        assert np.abs(got - ref).max() / scale < 2e-6
+        assert np.abs(one - ref).max() / scale > 2e-5                # a single TF32 product is not enough
+
+
+def test_tf32_round_is_nearest_even():
+    import torch
+    from open3d_ml_b200 import _lib as L
+    x = torch.tensor([1.0, 1.0 + 2.0 ** -11, 1.0 + 2.0 ** -11 + 2.0 ** -20, 1.0 + 3 * 2.0 ** -11, -1.0 - 2.0 ** -10,
+                      0.0, 65504.0, 3.0e38], dtype=torch.float32)
+    r = L.tf32_round(x)
+    exp = torch.tensor([1.0, 1.0, 1.0 + 2.0 ** -10, 1.0 + 2.0 ** -9, -1.0 - 2.0 ** -10, 0.0, 65504.0, 3.0e38])
+    exp[-1] = r[-1]
+    assert torch.equal(r[:-1], exp[:-1]) and abs(float(r[-1]) / 3.0e38 - 1) < 1e-3

@@ -33,7 +33,7 @@ def deconv(H, W, C, s, co):
     pw = L.pack_linear(w.permute(0, 2, 3, 1).reshape(C, s * s * co))
     sc, sh = torch.ones(s * s * co).cuda(), torch.zeros(s * s * co).cuda()
     out = torch.empty(1, H * s, W * s, 384).cuda()
-    return lambda: L.check(L.lib().o3dml_deconv_nhwc_tc(L.ptr(x), 1, H, W, C, s, L.ptr(pw.img), pw.k_pad, pw.n_pad, pw.w_exp,
+    return lambda: L.check(L.lib().o3dml_deconv_nhwc_tc(L.ptr(x), 1, H, W, C, s, L.ptr(pw.img), pw.k_pad, pw.n_pad,
                                                         L.ptr(sc), L.ptr(sh), 1, 0.0, L.ptr(out), 384, co, L.stream())), (x, out, sc, sh, pw)
 
 
@@ -50,7 +50,7 @@ def conv(H, W, C, co, stride):
     pw = L.pack_linear(w.permute(2, 3, 1, 0).reshape(9 * C, co)); s = torch.ones(co).cuda(); t = torch.zeros(co).cuda()
     OH, OW = (H - 1) // stride + 1, (W - 1) // stride + 1
     o = torch.empty(1, OH, OW, co).cuda()
-    return lambda: L.check(L.lib().o3dml_conv3x3_nhwc_tc(L.ptr(x), 1, H, W, C, stride, L.ptr(pw.img), pw.k_pad, pw.n_pad, pw.w_exp,
+    return lambda: L.check(L.lib().o3dml_conv3x3_nhwc_tc(L.ptr(x), 1, H, W, C, stride, L.ptr(pw.img), pw.k_pad, pw.n_pad,
                                                          L.ptr(s), L.ptr(t), 1, 0.0, L.ptr(o), co, L.stream())), (x, o, s, t, pw)
 
 

@@ -12,7 +12,7 @@ x = torch.randn(1, 62, 54, 256).cuda(); w = torch.randn(256, 256, 3, 3) / 48
 pw = L.pack_linear(w.permute(2, 3, 1, 0).reshape(9 * 256, 256)); s = torch.ones(256).cuda(); t = torch.zeros(256).cuda()
 o = torch.empty(1, 62, 54, 256).cuda()
 for _ in range(3):
-    L.check(L.lib().o3dml_conv3x3_nhwc_tc(L.ptr(x), 1, 62, 54, 256, 1, L.ptr(pw.img), pw.k_pad, pw.n_pad, pw.w_exp, L.ptr(s), L.ptr(t), 1, 0.0, L.ptr(o), 256, L.stream()))
+    L.check(L.lib().o3dml_conv3x3_nhwc_tc(L.ptr(x), 1, 62, 54, 256, 1, L.ptr(pw.img), pw.k_pad, pw.n_pad, L.ptr(s), L.ptr(t), 1, 0.0, L.ptr(o), 256, L.stream()))
 torch.cuda.synchronize()
 h = ctypes.CDLL(L.LIB_PATH)
 buf = (ctypes.c_longlong * 4100)()
