@@ -103,6 +103,20 @@ O3DML_API int o3dml_radius_fill(const float* queries, int64_t num_points, int64_
                       float* neighbors_distance2, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* Per-voxel reduction over the CSR voxel lists of o3dml_voxelize: the second half of
+ *   open3d.ml.contrib.subsample / subsample_batch (barycentre grid subsampling,
+ *   ml3d/datasets/utils/dataprocessing.py:14-49, ml3d/torch/models/kpconv.py:2037-2164) and of
+ *   open3d.ml.torch.ops.voxel_pooling (position_fn / feature_fn in {average, max, nearest}).
+ * out_points [M,3] (may be NULL), out_features [M,F], out_labels [M] int32 = most frequent label of the
+ * voxel (ties: smallest).  Modes: 0 mean (sequential fp32 sum in ascending point id, then one divide),
+ * 1 max, 2 first point of the voxel.  d_num_voxels may be NULL (= num_voxels_bound). */
+O3DML_API int o3dml_voxel_reduce(const float* points, int point_stride, const float* features,
+                                 int feat_channels, int feat_stride, const int32_t* labels,
+                                 const int64_t* voxel_row_splits, const int64_t* voxel_point_indices,
+                                 const int64_t* d_num_voxels, int64_t num_voxels_bound, int position_mode,
+                                 int feature_mode, float* out_points, float* out_features,
+                                 int32_t* out_labels, void* stream);
+
 /* ------------------------------------------------------- PointPillars ---- */
 
 /* PillarFeatureNet.forward + PFNLayer.forward + PointPillarsScatter.forward fused

@@ -18,10 +18,18 @@
 //   * gathered sources (index / batch-relative index / shadow rows) by 16-byte cp.async into the same
 //     128-byte-swizzled layout,
 //   * the weight slices (hi and lo image) by two more tensor copies.
-// The 8 converter warps then only run  hi = x & mask, lo = x - hi  over the tile in place (44 instructions
-// per thread and slice against 357 + 686 in round 1) and publish it to the async proxy.
+// The 8 converter warps then only run  hi = x & mask, lo = x - hi  on their row (45 instructions per
+// thread and slice against 357 + 686 in round 1) and store both parts into TENSOR MEMORY
+// (tcgen05.st): the MMAs take A from TMEM (.kind::tf32 [d], [a], b-desc) and only W from shared memory.
+// Why: an SS-mode 128x128x8 MMA reads 8 KB of shared memory in its 64 cycles, i.e. it saturates the
+// 128 B/clk shared-memory port on its own; the first round-2 version (A hi/lo rewritten in shared
+// memory) measured ~1 500 cycles per slice because the TMA fills (48 KB), the converter traffic (48 KB)
+// and the operand reads (96 KB) all queue on that port.  With A in TMEM a slice moves 48 KB of fills,
+// 16 KB of converter reads and 48 KB of W reads: 875 cycles against 768 of MMA issue.
 // Shared-memory layout: K-major, SWIZZLE_128B (row r, 16-byte chunk c at r*128 + ((c ^ (r & 7)) << 4)),
 // UMMA descriptors with SBO = 1024, K advanced by +32 B per MMA (K = 8 TF32).
+// TMEM layout: columns [0, 2 BN) two accumulator buffers, then per stage 32 columns of A-hi and 32 of
+// A-lo (lane = row, column = k: the M = 128 A-fragment layout of the TS-mode MMA).
 //
 // TMEM accumulation truncates (measured round 1), hence every GT_FLUSH slices the accumulator is folded
 // into fp32 registers with round-to-nearest adds while the next chunk runs in the other TMEM buffer.
@@ -38,7 +46,7 @@ __device__ long long g_gt_dbg[8192];
 
 constexpr int GT_ROWS = 128;
 constexpr int GT_KS = 32;        // fp32 channels per k-slice (= one 128-byte swizzle row)
-constexpr int GT_FLUSH = 8;      // k-slices (256 channels) per TMEM accumulation chunk
+constexpr int GT_FLUSH = 4;      // k-slices (128 channels = 48 accumulating MMAs) per TMEM accumulation chunk
 constexpr int GT_MAX_SRC = 3;
 constexpr int GT_CONV_THREADS = 256;   // warps 0-7: converters + flush + epilogue
 constexpr int GT_LOADERS = 128;        // warps 10-13 (GATHER kernels only)
@@ -159,19 +167,44 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         : "memory");
 }
 
+// TS mode: A from tensor memory (lane = row, one column per TF32 element), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> TMEM: 32 lanes x 32 bit, 16 consecutive columns per thread (lane = 32 * (warp % 4) + lane id)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <int BN>
 struct GtCfg {
     static constexpr int B_BYTES = BN * 128;                       // one of hi/lo per stage
-    static constexpr int STAGE = 2 * GT_A_BYTES + 2 * B_BYTES;     // multiples of 1024 (swizzle atom alignment)
-    static constexpr int STAGES = BN >= 128 ? 3 : (BN >= 64 ? 4 : 5);
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;    // two accumulator buffers
+    static constexpr int STAGE = GT_A_BYTES + 2 * B_BYTES;         // raw A + W hi + W lo; multiples of 1024
+    static constexpr int STAGES = BN >= 128 ? 4 : 5;
+    static constexpr int A_COL0 = 2 * BN;                          // TMEM: accumulators first, then the A slots
+    static constexpr int TMEM_COLS = 512;                          // 2 * BN + STAGES * 64 <= 512, power of two
+    static_assert(2 * BN + STAGES * 64 <= 512, "TMEM budget");
+    static_assert(STAGES <= GT_FLUSH + 1, "a chunk must be folded before its TMEM buffer is reused");
     static constexpr int TAIL = GT_MAX_SRC * GT_ROWS * 8 + GT_ROWS * 8 + 256;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE + TAIL + 1024;
 };
 
 // Pipeline (per CTA, one [128 x BN] output tile, k-slices of 32 channels through a ring of stages):
-//   warps 0-7     converters: wait full[stage], rewrite the raw A tile as (hi, lo) in place, proxy fence,
-//                 arrive conv[stage]; fold finished TMEM chunks into registers; epilogue (TMEM -> BN /
+//   warps 0-7     converters: wait full[stage], split their row of the raw A tile into (hi, lo), tcgen05.st
+//                 into the stage's TMEM slot, arrive conv[stage]; fold finished TMEM chunks into registers;
+//                 epilogue (TMEM -> BN /
 //                 residual / activation -> shared-memory staged, row-coalesced stores)
 //   warp 8        MMA issuer: waits conv[stage], one elected lane issues 12 tcgen05.mma (4 k-steps x 3
 //                 products), tcgen05.commit -> empty[stage] (+ chunk[] at chunk ends); owns the TMEM allocation
@@ -269,21 +302,19 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             const long long tm1 = clock64();
 #endif
             if (elect_one()) {
-                const uint32_t ah0 = stage0 + (uint32_t)stage * C::STAGE;
-                const uint32_t al0 = ah0 + GT_A_BYTES;
-                const uint32_t bh0 = al0 + GT_A_BYTES;
+                const uint32_t bh0 = stage0 + (uint32_t)stage * C::STAGE + GT_A_BYTES;
                 const uint32_t bl0 = bh0 + C::B_BYTES;
+                const uint32_t a_hi = tmem + (uint32_t)(C::A_COL0 + stage * 64);
+                const uint32_t a_lo = a_hi + 32;
                 const uint32_t acc = tmem + (uint32_t)((chunk & 1) * BN);
                 const bool first = (s % GT_FLUSH) == 0;
 #pragma unroll
-                for (int ks = 0; ks < GT_KS / 8; ++ks) {        // K = 8 TF32 = 32 bytes per MMA
-                    const uint64_t ah = smem_desc_sw128(ah0 + ks * 32);
-                    const uint64_t al = smem_desc_sw128(al0 + ks * 32);
+                for (int ks = 0; ks < GT_KS / 8; ++ks) {        // K = 8 TF32 = 8 TMEM columns / 32 bytes of W per MMA
                     const uint64_t bh = smem_desc_sw128(bh0 + ks * 32);
                     const uint64_t bl = smem_desc_sw128(bl0 + ks * 32);
-                    umma_tf32(acc, ah, bh, idesc, !(first && ks == 0));
-                    umma_tf32(acc, ah, bl, idesc, 1);
-                    umma_tf32(acc, al, bh, idesc, 1);
+                    umma_tf32_ts(acc, a_hi + ks * 8, bh, idesc, !(first && ks == 0));
+                    umma_tf32_ts(acc, a_hi + ks * 8, bl, idesc, 1);
+                    umma_tf32_ts(acc, a_lo + ks * 8, bh, idesc, 1);
                 }
                 tc::umma_commit(&empty_bar[stage]);
                 if ((s % GT_FLUSH) == GT_FLUSH - 1 || s == nsl - 1) tc::umma_commit(&chunk_bar[chunk & 1]);
@@ -309,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                     a_tma = p.src[sidx].index == nullptr;
                 }
                 const uint32_t ah = stage0 + (uint32_t)stage * C::STAGE;
-                const uint32_t bh = ah + 2 * GT_A_BYTES;
+                const uint32_t bh = ah + GT_A_BYTES;
                 mbar_arrive_expect_tx(&full_bar[stage], 2 * C::B_BYTES + (a_tma ? GT_A_BYTES : 0));
                 tma_load_2d(bh, &p.mapB, k0, col0, &full_bar[stage]);
                 tma_load_2d(bh + C::B_BYTES, &p.mapB, k0, p.Npad + col0, &full_bar[stage]);
@@ -390,31 +421,35 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         for (int s = 0; s < nsl; ++s) {
             const int stage = s % S, use = s / S;
             // a chunk whose last slice is at least S slices behind has certainly drained (its stage was reused);
-            // it is folded before slice (chunk + 2) * GT_FLUSH reuses its TMEM buffer (S <= GT_FLUSH)
+            // it is folded before slice (chunk + 2) * GT_FLUSH reuses its TMEM buffer (S - 1 <= GT_FLUSH)
             while (next_flush < last_chunk && s >= (next_flush + 1) * GT_FLUSH + S - 1) fold(next_flush++);
 #ifdef O3DML_DEBUG_TIMING
             const long long tq0 = clock64();
 #endif
             tc::mbar_wait(&full_bar[stage], use & 1);
+            tc::tc_fence_after();       // the MMAs that read this stage's TMEM slot completed (empty -> TMA -> full)
 #ifdef O3DML_DEBUG_TIMING
             const long long tq1 = clock64();
 #endif
-            uint8_t* a_hi = stages + (size_t)stage * C::STAGE;
-            uint8_t* a_lo = a_hi + GT_A_BYTES;
+            // this thread's row, k-half `grp` (4 of the row's 8 swizzled 16-byte chunks) -> hi / lo -> TMEM
+            const uint8_t* a_row = stages + (size_t)stage * C::STAGE + (size_t)rt * 128;
+            uint32_t hi[16], lo[16];
 #pragma unroll
-            for (int j = 0; j < GT_A_BYTES / 16 / GT_CONV_THREADS; ++j) {      // 1024 words of 16 B, 4 per thread
-                const uint32_t off = (uint32_t)(tid + j * GT_CONV_THREADS) * 16u;
-                const uint4 v = *reinterpret_cast<const uint4*>(a_hi + off);
-                uint4 h, l;
-                h.x = v.x & 0xFFFFE000u; h.y = v.y & 0xFFFFE000u; h.z = v.z & 0xFFFFE000u; h.w = v.w & 0xFFFFE000u;
-                l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-                l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-                l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-                l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
-                *reinterpret_cast<uint4*>(a_hi + off) = h;
-                *reinterpret_cast<uint4*>(a_lo + off) = l;
+            for (int j = 0; j < 4; ++j) {
+                const int cch = grp * 4 + j;
+                const uint4 v = *reinterpret_cast<const uint4*>(a_row + (((cch ^ (rt & 7))) << 4));
+                const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    hi[4 * j + u] = x[u] & 0xFFFFE000u;
+                    lo[4 * j + u] = __float_as_uint(__uint_as_float(x[u]) - __uint_as_float(hi[4 * j + u]));
+                }
             }
-            tc::fence_async_smem();
+            const uint32_t a_slot = tmem_lane + (uint32_t)(C::A_COL0 + stage * 64 + grp * 16);
+            tmem_st16(a_slot, hi);
+            tmem_st16(a_slot + 32, lo);
+            tmem_st_wait();
+            tc::tc_fence_before();
             mbar_arrive(&conv_bar[stage]);
 #ifdef O3DML_DEBUG_TIMING
             if (dbg && tid == 0 && s < 450) {

@@ -202,42 +202,44 @@ class KPFCNNB200:
     __call__ = forward
 
 
-def build_batch(clouds, cfg, device="cuda"):
-    """The index pyramid of KPConvBatch.segmentation_inputs (ml3d/torch/dataloaders/concat_batcher.py:
-    186-305) for a list of (points [n,3], features [n,F]) numpy clouds: per level the conv / pool /
-    upsample neighbour matrices, built with the CUDA fixed-radius search and padded with the shadow id
-    (kpconv.py:2002-2034).  Grid subsampling (a "next" row) uses the numpy barycentre
-    stand-in of open3d_ml_b200.synth.  Returns a dict of CUDA tensors."""
+def build_batch(clouds, cfg, device="cuda", neighborhood_limits=None, timings=None):
+    """KPConvBatch.segmentation_inputs (ml3d/torch/dataloaders/concat_batcher.py:186-305) on the device for a
+    list of (points [n,3], features [n,F]) numpy clouds: the clouds are stacked once, then per level
+      conv neighbours   batch_neighbors(P, P, r)            (kpconv.py:2002-2034)
+      sub-sampled cloud batch_grid_subsampling(P, dl = 2 r / conv_radius), barycentre per voxel (:2037-2164)
+      pool / upsample   batch_neighbors(Q, P, r), batch_neighbors(P, Q, 2 r)
+    all with the CUDA fixed-radius search / voxelize / voxel_reduce kernels (13 searches + 4 subsamplings for
+    the 5-level S3DIS config), padded with the shadow id and cropped by `neighborhood_limits` like
+    big_neighborhood_filter (:175-186).  Returns a dict of CUDA tensors (indices int64 as the reference)."""
     import numpy as np
-    from . import ops, synth
+    from . import ops
 
-    def neighbors(queries, supports, q_lens, s_lens, radius):
-        qs = torch.tensor(np.concatenate([[0], np.cumsum(q_lens)]), dtype=torch.int64, device=device)
-        ss = torch.tensor(np.concatenate([[0], np.cumsum(s_lens)]), dtype=torch.int64, device=device)
+    def neighbors(queries, supports, qs, ss, radius, limit=None):
         r = ops.fixed_radius_search(supports, queries, radius, ss, qs, return_distances=False)
         rs = r.neighbors_row_splits
         width = int((rs[1:] - rs[:-1]).max()) if rs.numel() > 1 else 0
+        if limit is not None:
+            width = min(width, int(limit))
         return ops.ragged_to_dense(r.neighbors_index, rs, width,
                                    torch.tensor([supports.shape[0]], dtype=torch.int32)).to(torch.int64)
 
+    lim = list(neighborhood_limits) if neighborhood_limits else None
     r = cfg["first_subsampling_dl"] * cfg["conv_radius"]
-    dl = cfg["first_subsampling_dl"]
     out = dict(features=torch.from_numpy(np.concatenate([c[1] for c in clouds])).to(device),
                points=[], neighbors=[], pools=[], upsamples=[], lengths=[])
-    cur = [c[0] for c in clouds]
+    P = torch.from_numpy(np.concatenate([c[0] for c in clouds]).astype(np.float32)).to(device)
+    rs = torch.tensor(np.concatenate([[0], np.cumsum([len(c[0]) for c in clouds])]), dtype=torch.int64,
+                      device=device)
     for lvl in range(cfg["num_layers"]):
-        P = torch.from_numpy(np.concatenate(cur)).to(device)
-        ln = [len(c) for c in cur]
         out["points"].append(P)
-        out["lengths"].append(ln)
-        out["neighbors"].append(neighbors(P, P, ln, ln, r))
+        out["lengths"].append((rs[1:] - rs[:-1]).to(torch.int32))
+        out["neighbors"].append(neighbors(P, P, rs, rs, r, lim[lvl] if lim else None))
         if lvl < cfg["num_layers"] - 1:
-            nxt = [synth.grid_subsample(c, 2 * dl) for c in cur]
-            Q = torch.from_numpy(np.concatenate(nxt)).to(device)
-            lq = [len(c) for c in nxt]
-            out["pools"].append(neighbors(Q, P, lq, ln, r))
-            out["upsamples"].append(neighbors(P, Q, ln, lq, 2 * r))
-            cur, dl, r = nxt, 2 * dl, r * 2
+            dl = 2 * r / cfg["conv_radius"]
+            Q, qs, _, _ = ops.subsample_batch_cuda(P, rs, sampleDl=dl)
+            out["pools"].append(neighbors(Q, P, qs, rs, r, lim[lvl] if lim else None))
+            out["upsamples"].append(neighbors(P, Q, rs, qs, 2 * r, lim[lvl + 1] if lim else None))
+            P, rs, r = Q, qs, r * 2
         else:
             out["pools"].append(torch.zeros((0, 1), dtype=torch.int64, device=device))
             out["upsamples"].append(torch.zeros((0, 1), dtype=torch.int64, device=device))

@@ -249,3 +249,77 @@ class NearestNeighborSearch:
         n = q.shape[0]
         return (_O3CTensor(r.neighbors_index.reshape(n, knn)),
                 _O3CTensor(r.neighbors_distance.reshape(n, knn)))
+
+
+# ------------------------------------------------------------------ grid subsampling
+def voxel_reduce(points, features, labels, vrs, pidx, counts=None, num_voxels=None,
+                 position_mode=0, feature_mode=0, want_points=True):
+    """Per-voxel mean / max / first over CSR voxel lists (o3dml_voxel_reduce).  All CUDA tensors."""
+    m = int(num_voxels if num_voxels is not None else vrs.numel() - 1)
+    dev = points.device
+    F = 0 if features is None else features.shape[1]
+    op = torch.empty((m, 3), dtype=torch.float32, device=dev) if want_points else None
+    of = torch.empty((m, F), dtype=torch.float32, device=dev) if F else None
+    ol = torch.empty((m,), dtype=torch.int32, device=dev) if labels is not None else None
+    L.check(L.lib().o3dml_voxel_reduce(
+        L.ptr(points), points.stride(0), L.ptr(features), F, features.stride(0) if F else 0, L.ptr(labels),
+        L.ptr(vrs), L.ptr(pidx), L.ptr(counts), m, int(position_mode), int(feature_mode), L.ptr(op), L.ptr(of),
+        L.ptr(ol), L.stream()))
+    return op, of, ol
+
+
+def _subsample_range(pts, dl):
+    """Grid origin = floor(min / dl) * dl (float32), upper bound = max: ONE device->host read."""
+    mm = torch.stack([pts.amin(0), pts.amax(0)]).cpu().numpy().astype(np.float32)
+    dl = np.float32(dl)
+    origin = (np.floor((mm[0] / dl).astype(np.float32)) * dl).astype(np.float32)
+    return origin, mm[1]
+
+
+def subsample_batch_cuda(points, row_splits, features=None, classes=None, sampleDl=0.1, max_p=0):
+    """Grid subsampling of a stacked batch on the device: CUDA tensors in, CUDA tensors out.
+    Returns (s_points [M,3], s_row_splits int64 [B+1], s_features or None, s_labels or None)."""
+    _check_points(points)
+    pts = _dev(points).contiguous()
+    if pts.shape[0] == 0:
+        raise RuntimeError("subsample: empty point cloud")
+    rs = _splits(row_splits, pts.shape[0], pts.device)
+    origin, mx = _subsample_range(pts, sampleDl)
+    dl = float(sampleDl)
+    coords, pidx, vrs, bsp, _, counts = voxelize_raw(pts, rs, [dl, dl, dl], origin, mx, INT64_MAX,
+                                                     int(max_p) if max_p and max_p > 0 else INT64_MAX)
+    m = int(counts[0].item())
+    feats = None if features is None else _dev(features).to(torch.float32).contiguous()
+    labs = None if classes is None else _dev(classes).to(torch.int32).contiguous().view(-1)
+    if feats is not None and feats.dim() == 1:
+        feats = feats.view(-1, 1)
+    op, of, ol = voxel_reduce(pts, feats, labs, vrs, pidx, counts, m)
+    return op, bsp, of, ol
+
+
+def subsample_batch(points, batches_len, features=None, classes=None, sampleDl=0.1, method="barycenter",
+                    max_p=0, verbose=0):
+    """open3d.ml.contrib.subsample_batch (ml3d/torch/models/kpconv.py:2096-2164): numpy in, numpy out.
+    Returns (s_points, s_len[, s_features][, s_labels]) exactly like the call sites unpack it."""
+    if method != "barycenter":
+        raise RuntimeError("subsample_batch: only method='barycenter' is implemented")
+    pts = torch.as_tensor(np.ascontiguousarray(points, dtype=np.float32))
+    lens = np.asarray(batches_len, dtype=np.int64).reshape(-1)
+    rs = torch.as_tensor(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64))
+    f = None if features is None else torch.as_tensor(np.ascontiguousarray(features, dtype=np.float32))
+    c = None if classes is None else torch.as_tensor(np.ascontiguousarray(classes).astype(np.int32))
+    op, bsp, of, ol = subsample_batch_cuda(pts, rs, f, c, sampleDl, max_p)
+    out = [op.cpu().numpy(), np.diff(bsp.cpu().numpy()).astype(np.int32)]
+    if of is not None:
+        out.append(of.cpu().numpy())
+    if ol is not None:
+        lab = ol.cpu().numpy()
+        out.append(lab.astype(np.asarray(classes).dtype, copy=False))
+    return tuple(out)
+
+
+def subsample(points, features=None, classes=None, sampleDl=0.1, verbose=0):
+    """open3d.ml.contrib.subsample (ml3d/datasets/utils/dataprocessing.py:14-49): one cloud."""
+    r = subsample_batch(points, [len(points)], features, classes, sampleDl)
+    out = (r[0],) + tuple(r[2:])
+    return out[0] if len(out) == 1 else out

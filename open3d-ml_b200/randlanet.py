@@ -34,9 +34,14 @@ def _fold_bn(sd, prefix, bias=None, eps=BN_EPS):
 
 
 class RandLANetB200:
-    def __init__(self, state_dict, num_layers=4, num_neighbors=16, device=None, use_tc=None):
+    def __init__(self, state_dict, num_layers=4, num_neighbors=16, device=None, use_tc=None,
+                 sub_sampling_ratio=None, use_graph=None):
         L.require_cuda()
         import os
+        self.sub_sampling_ratio = list(sub_sampling_ratio or [4] * num_layers)
+        self.use_graph = (os.environ.get("O3DML_RL_GRAPH", "1") != "0") if use_graph is None else bool(use_graph)
+        self._graphs = {}
+        self._splits = {}
         self.use_tc = (os.environ.get("O3DML_LFA_TC", "1") != "0") if use_tc is None else bool(use_tc)
         self.device = torch.device(device or "cuda")
         self.num_layers = num_layers
@@ -233,11 +238,123 @@ class RandLANetB200:
 
     __call__ = forward
 
+    # ------------------------------------------------------ device-side transform
+    def _row_splits(self, B, n):
+        key = (B, n)
+        t = self._splits.get(key)
+        if t is None:
+            t = torch.arange(0, (B + 1) * n, n, dtype=torch.int64, device=self.device)
+            self._splits[key] = t
+        return t
+
+    def _knn(self, points, queries, k, ps, qs, name):
+        """o3dml_knn_search into cached int32 buffers (global row ids), no host synchronisation."""
+        nq = queries.shape[0]
+        idx = self._geti(name, nq, k)
+        batch = ps.numel() - 1
+        wsb = L.lib().o3dml_knn_workspace_bytes(points.shape[0], nq, batch)
+        ws = self._getb(name + ".ws", wsb)
+        L.check(L.lib().o3dml_knn_search(L.ptr(points), points.shape[0], L.ptr(ps), L.ptr(queries), nq,
+                                         L.ptr(qs), batch, k, L.ptr(idx), 0, None, L.ptr(ws), wsb, L.stream()))
+        return idx
+
+    def _geti(self, name, rows, cols):
+        key = (name, rows, cols, "i32")
+        t = self._buf.get(key)
+        if t is None:
+            t = self._buf[key] = torch.empty((rows, cols), dtype=torch.int32, device=self.device)
+        return t
+
+    def _getb(self, name, nbytes):
+        key = (name, nbytes, "u8")
+        t = self._buf.get(key)
+        if t is None:
+            t = self._buf[key] = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        return t
+
+    def build_pyramid(self, points):
+        """The index pyramid of RandLANet.transform (randlanet.py:218-229: per level k-NN of the cloud in
+        itself, the first N/ratio points as the sub-sampled cloud, 1-NN of every point in the sub-sampled
+        cloud) for a [B, N, 3] CUDA tensor, built on the device with the batched grid k-NN
+        (o3dml_knn_search, bit-exact against the oracle).  Indices are int32 GLOBAL row ids of the stacked
+        [B*N, ...] buffers (the reference ships int64 batch-relative ids over PCIe: 80 of its 90 MB per
+        SemanticKITTI batch), so the batch is presented to forward() as ONE cloud of B*N points:
+        sub_idx is the per-cloud prefix of neighbor_indices, nothing is searched twice."""
+        B, n, _ = points.shape
+        pc = points.to(self.device, torch.float32).contiguous()
+        out = dict(coords=[], neighbor_indices=[], sub_idx=[], interp_idx=[])
+        for i in range(self.num_layers):
+            flat = pc.view(B * n, 3)
+            rs = self._row_splits(B, n)
+            nb = self._knn(flat, flat, self.k, rs, rs, "pyr.nb.%d" % i)
+            ns = n // self.sub_sampling_ratio[i]
+            sub = self._get("pyr.sub.%d" % i, B * ns, 3).view(B, ns, 3)
+            sub.copy_(pc[:, :ns])
+            pool = self._geti("pyr.pool.%d" % i, B * ns, self.k)
+            pool.view(B, ns, self.k).copy_(nb.view(B, n, self.k)[:, :ns])
+            up = self._knn(sub.view(B * ns, 3), flat, 1, self._row_splits(B, ns), rs, "pyr.up.%d" % i)
+            out["coords"].append(flat.view(1, B * n, 3))
+            out["neighbor_indices"].append(nb.view(1, B * n, self.k))
+            out["sub_idx"].append(pool.view(1, B * ns, self.k))
+            out["interp_idx"].append(up.view(1, B * n, 1))
+            pc, n = sub, ns
+        return out
+
+    def forward_points(self, points, features=None):
+        """transform + forward from raw clouds: points [B, N, 3] (host or device), features [B, N, C] or
+        None (= the coordinates, randlanet.py:204-207).  Only the points (and features) cross PCIe."""
+        pts = points.to(self.device, non_blocking=True)
+        B, N, _ = pts.shape
+        inp = self.build_pyramid(pts)
+        feat = pts if features is None else torch.cat([pts, features.to(self.device, non_blocking=True)], -1)
+        inp["features"] = feat.reshape(1, B * N, -1)
+        return self.forward(inp).view(B, N, self.num_classes)
+
+    # ------------------------------------------------------------- CUDA graph
+    def _graphed(self, name, tensors, thunk):
+        """Replays thunk() from a CUDA graph captured at first use for these tensor addresses (the
+        forward is ~40 launches of 5-60 us: launch-bound from Python at one cloud per GPU).  thunk must
+        be sync-free and allocation-stable (cached buffers); the result is cloned."""
+        if not self.use_graph:
+            return thunk()
+        key = (name,) + tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in tensors)
+        ent = self._graphs.get(key)
+        if ent is None:
+            thunk()                                        # sizes the cached buffers, sets kernel attributes
+            torch.cuda.current_stream().synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = L.lib().o3dml_launch_count()
+            with torch.cuda.graph(graph):
+                out = thunk()
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+            ent = self._graphs[key] = (graph, out, L.lib().o3dml_launch_count() - n0)
+        graph, out, launches = ent
+        graph.replay()
+        L.lib().o3dml_launch_count_add(launches)
+        return out.clone()
+
+    def forward_graphed(self, inputs):
+        """forward() for DEVICE-resident inputs, replayed from a CUDA graph keyed by their addresses."""
+        flat = [inputs["features"]] + [t for k in ("coords", "neighbor_indices", "sub_idx", "interp_idx")
+                                       for t in inputs[k]]
+        if not all(t.is_cuda for t in flat):
+            return self.forward(inputs)
+        return self._graphed("forward", flat, lambda: self.forward(inputs))
+
+    def forward_points_graphed(self, points, features=None):
+        """forward_points() for DEVICE-resident clouds, replayed from a CUDA graph (pyramid + forward)."""
+        if not points.is_cuda or (features is not None and not features.is_cuda):
+            return self.forward_points(points, features)
+        ts = [points] + ([features] if features is not None else [])
+        return self._graphed("forward_points", ts, lambda: self.forward_points(points, features))
+
 
 def patch_reference_model(model):
     """Drop-in: make an (unmodified) reference ``RandLANet`` instance run its forward on the
     fused CUDA path (keeps preprocess/transform/losses).  BN must be in eval mode."""
-    fused = RandLANetB200(model.state_dict(), model.cfg.num_layers, model.cfg.num_neighbors)
+    fused = RandLANetB200(model.state_dict(), model.cfg.num_layers, model.cfg.num_neighbors,
+                          sub_sampling_ratio=list(model.cfg.sub_sampling_ratio))
 
     def forward(inputs):
         if model.training:

@@ -112,10 +112,9 @@ def install(ml3d_root=None):
                       {"__init__": lambda self, *a, **k: _not_on_hot_path("layers.SparseConv")()})
     _module("open3d.ml.torch.layers", FixedRadiusSearch=O.FixedRadiusSearch, KNNSearch=O.KNNSearch,
             SparseConv=stub_layer, SparseConvTranspose=stub_layer)
-    _module("open3d.ml.contrib",
+    _module("open3d.ml.contrib", subsample=O.subsample, subsample_batch=O.subsample_batch,
             **{n: _not_on_hot_path("contrib." + n)
-               for n in ("subsample", "subsample_batch", "iou_bev_cpu", "iou_3d_cpu",
-                         "iou_bev_cuda", "iou_3d_cuda")})
+               for n in ("iou_bev_cpu", "iou_3d_cpu", "iou_bev_cuda", "iou_3d_cuda")})
     vis = _module("open3d.visualization")
     tb = _module("open3d.visualization.tensorboard_plugin")
     _module("open3d.visualization.tensorboard_plugin.summary")

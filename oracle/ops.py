@@ -236,3 +236,72 @@ def np_radius(points, queries, radius, points_row_splits=None, queries_row_split
     idx = np.concatenate(rows_i) if rows_i else np.zeros(0, np.int32)
     d2 = np.concatenate(rows_d) if rows_d else np.zeros(0, np.float32)
     return idx.astype(np.int32), rs, d2.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------
+# grid subsampling (contract: ops_ref.c, "grid subsampling")
+# ----------------------------------------------------------------------------
+def subsample_range(points, dl):
+    """range_min / range_max of the voxel grid: origin = floor(min / dl) * dl in float32."""
+    points = _f32(points)
+    dl = np.float32(dl)
+    mn, mx = points.min(0), points.max(0)
+    origin = (np.floor((mn / dl).astype(np.float32)) * dl).astype(np.float32)
+    return origin, mx.astype(np.float32)
+
+
+def c_subsample_batch(points, batches_len, features=None, classes=None, sampleDl=0.1, max_p=0):
+    """-> (s_points [M,3], s_len [B] int32, [s_features [M,F]], [s_labels [M] int32])."""
+    points = _f32(points)
+    rs = np.concatenate([[0], np.cumsum(np.asarray(batches_len, np.int64))]).astype(np.int64)
+    origin, mx = subsample_range(points, sampleDl)
+    vox = c_voxelize(points, rs, [sampleDl] * 3, origin, mx, 2**62, max_p if max_p > 0 else 2**62)
+    M = len(vox["voxel_coords"])
+    F = 0 if features is None else features.shape[1]
+    feats = None if features is None else _f32(features)
+    labs = None if classes is None else np.ascontiguousarray(classes, np.int32).reshape(-1)
+    op = np.empty((M, 3), np.float32)
+    of = np.empty((M, F), np.float32) if F else None
+    ol = np.empty((M,), np.int32) if labs is not None else None
+    rc = lib().oracle_voxel_reduce(
+        _p(points, ctypes.c_float), ctypes.c_int(3), _p(feats, ctypes.c_float) if F else None, ctypes.c_int(F),
+        _p(labs, ctypes.c_int32) if labs is not None else None, _p(vox["voxel_point_row_splits"], ctypes.c_int64),
+        _p(vox["voxel_point_indices"], ctypes.c_int64), ctypes.c_int64(M), ctypes.c_int(0), ctypes.c_int(0),
+        _p(op, ctypes.c_float), _p(of, ctypes.c_float) if F else None, _p(ol, ctypes.c_int32) if ol is not None else None)
+    assert rc == 0
+    out = [op, np.diff(vox["voxel_batch_splits"]).astype(np.int32)]
+    if F:
+        out.append(of)
+    if ol is not None:
+        out.append(ol)
+    return tuple(out)
+
+
+def np_subsample_batch(points, batches_len, features=None, classes=None, sampleDl=0.1, max_p=0):
+    """numpy restatement of c_subsample_batch (independent code path: np_voxelize + python loops)."""
+    points = _f32(points)
+    rs = np.concatenate([[0], np.cumsum(np.asarray(batches_len, np.int64))]).astype(np.int64)
+    origin, mx = subsample_range(points, sampleDl)
+    vox = np_voxelize(points, rs, [sampleDl] * 3, origin, mx, 2**62, max_p if max_p > 0 else 2**62)
+    vrs, pidx = vox["voxel_point_row_splits"], vox["voxel_point_indices"]
+    M = len(vox["voxel_coords"])
+
+    def mean(src):
+        out = np.empty((M, src.shape[1]), np.float32)
+        for v in range(M):
+            acc = np.zeros(src.shape[1], np.float32)
+            for j in pidx[vrs[v]:vrs[v + 1]]:
+                acc = (acc + src[j]).astype(np.float32)
+            out[v] = (acc / np.float32(vrs[v + 1] - vrs[v])).astype(np.float32)
+        return out
+    out = [mean(points), np.diff(vox["voxel_batch_splits"]).astype(np.int32)]
+    if features is not None:
+        out.append(mean(_f32(features)))
+    if classes is not None:
+        labs = np.asarray(classes, np.int32).reshape(-1)
+        ol = np.empty(M, np.int32)
+        for v in range(M):
+            vals, cnt = np.unique(labs[pidx[vrs[v]:vrs[v + 1]]], return_counts=True)
+            ol[v] = vals[np.argmax(cnt)]          # np.unique sorts: first maximum = smallest label
+        out.append(ol)
+    return tuple(out)

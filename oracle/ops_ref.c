@@ -231,3 +231,48 @@ EXPORT int oracle_voxelize(const float *points, const int64_t *row_splits, int64
     *num_kept = L;
     return 0;
 }
+
+/* ------------------------------------------------------- grid subsampling ---- */
+/* Per-voxel reduction over CSR voxel lists (the second half of open3d.ml.contrib.subsample /
+ * subsample_batch, call sites ml3d/datasets/utils/dataprocessing.py:14-49 and
+ * ml3d/torch/models/kpconv.py:2037-2164; upstream = KPConv's grid_subsampling.cpp, barycentre
+ * method).  PARITY UNPINNED (no golden vectors in the reference).  Contract fixed here:
+ *   - voxels come from oracle_voxelize with range_min = floor(min(points) / dl) * dl over ALL batch
+ *     items, range_max = max(points), no caps -> ascending linear index per batch item;
+ *   - barycentre / feature mean = sequential float32 sum in ascending point id, one division;
+ *   - label = most frequent label of the voxel, ties -> smallest label.
+ * mode: 0 mean, 1 max, 2 first. */
+EXPORT int oracle_voxel_reduce(const float *points, int point_stride, const float *features, int F,
+                               const int32_t *labels, const int64_t *vrs, const int64_t *pidx,
+                               int64_t M, int pos_mode, int feat_mode, float *out_points,
+                               float *out_features, int32_t *out_labels) {
+    for (int64_t v = 0; v < M; ++v) {
+        int64_t s = vrs[v], e = vrs[v + 1];
+        for (int c = 0; c < 3 + F; ++c) {
+            int is_pos = c < 3;
+            int mode = is_pos ? pos_mode : feat_mode;
+            volatile float acc = mode == 1 ? -INFINITY : 0.f;
+            for (int64_t j = s; j < e; ++j) {
+                float x = is_pos ? points[pidx[j] * point_stride + c] : features[pidx[j] * F + (c - 3)];
+                if (mode == 0) acc = acc + x;
+                else if (mode == 1) acc = x > acc ? x : acc;
+                else if (j == s) acc = x;
+            }
+            if (mode == 0) acc = acc / (float)(e - s);
+            if (is_pos) { if (out_points) out_points[v * 3 + c] = acc; }
+            else out_features[v * F + (c - 3)] = acc;
+        }
+        if (labels) {
+            int32_t best = 0;
+            int64_t best_n = 0;
+            for (int64_t i = s; i < e; ++i) {
+                int32_t l = labels[pidx[i]];
+                int64_t n = 0;
+                for (int64_t j = s; j < e; ++j) n += labels[pidx[j]] == l;
+                if (n > best_n || (n == best_n && l < best)) { best = l; best_n = n; }
+            }
+            out_labels[v] = best;
+        }
+    }
+    return 0;
+}

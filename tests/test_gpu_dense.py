@@ -181,7 +181,7 @@ def test_linear_tc_is_magnitude_independent(mag):
     x, w = rnd(n, cin, seed=1) * mag, rnd(cin, cout, seed=2) * 1e-3
     out = torch.empty(n, cout).cuda()
     L.linear([L.make_src(x)], L.pack_linear(w), out, act=None)
-    assert rel_err(out, x.double() @ w.double()) < 2e-6
+    assert rel_err(out, x.double() @ w.double()) < 3e-6
 
 
 ROW_SHAPES = [(3, 0, 8), (8, 0, 8), (16, 0, 8), (16, 0, 16), (16, 8, 32), (32, 0, 32), (64, 0, 32), (64, 0, 64),
@@ -246,7 +246,7 @@ def test_linear_tc_three_sources_mixed_tma_and_gather():
     L.linear([L.make_src(a), L.make_src(b, index=nb, index_ld=3), L.make_src(c)], L.pack_linear(w), out, act=None)
     bz = torch.cat([b, torch.zeros(1, 32).cuda()])[nb[:, 0]]
     ref = torch.cat([a, bz, c], 1).double() @ w.double()
-    assert rel_err(out, ref) < 2e-6
+    assert rel_err(out, ref) < 3e-6
 
 
 def test_linear_tc_strided_source_view():
@@ -255,4 +255,4 @@ def test_linear_tc_strided_source_view():
     w = rnd(64, 128, seed=2) / 8
     out = torch.empty(5000, 128).cuda()
     L.linear([L.make_src(wide[:, 32:], channels=64, ld=96)], L.pack_linear(w), out, act=None)
-    assert rel_err(out, wide[:, 32:].double() @ w.double()) < 2e-6
+    assert rel_err(out, wide[:, 32:].double() @ w.double()) < 3e-6

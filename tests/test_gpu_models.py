@@ -192,3 +192,55 @@ def test_pipelined_runner_matches_direct_calls():
     got2 = [r.clone() for r in runner.run(iter(pinned[::-1]))]
     for g, w in zip(got2, want[::-1]):
         assert torch.equal(g, w)
+
+
+# ------------------------------------------------------------------ device-side transforms (f1)
+def test_kpconv_build_batch_on_device_matches_oracle_pyramid():
+    """kpconv.build_batch = KPConvBatch.segmentation_inputs on the GPU (radius searches + grid
+    subsampling): points of every level and the three index matrices equal the CPU oracle's."""
+    from open3d_ml_b200.kpconv import build_batch
+    from oracle import ops as O
+    _, extra = H.state_dict("kpconv_s3dis.manifest.json", 5)
+    cfg = extra["cfg"]
+    clouds = [synth.room_cloud(9000, 80, room=(3.0, 2.5, 2.0)), synth.room_cloud(6000, 81, room=(3.0, 2.5, 2.0))]
+    b = build_batch(clouds, cfg)
+    P = np.concatenate([c[0] for c in clouds])
+    lens = [len(c[0]) for c in clouds]
+    r = cfg["first_subsampling_dl"] * cfg["conv_radius"]
+    for lvl in range(cfg["num_layers"]):
+        assert np.array_equal(b["points"][lvl].cpu().numpy(), P)
+        assert list(b["lengths"][lvl].cpu().numpy()) == list(lens)
+        assert np.array_equal(b["neighbors"][lvl].cpu().numpy(), MT.kp_batch_neighbors(P, P, lens, lens, r))
+        if lvl < cfg["num_layers"] - 1:
+            Q, ql = O.c_subsample_batch(P, lens, None, None, 2 * r / cfg["conv_radius"])
+            assert np.array_equal(b["pools"][lvl].cpu().numpy(), MT.kp_batch_neighbors(Q, P, ql, lens, r))
+            assert np.array_equal(b["upsamples"][lvl].cpu().numpy(), MT.kp_batch_neighbors(P, Q, lens, ql, 2 * r))
+            P, lens, r = Q, list(ql), 2 * r
+
+
+def test_randlanet_forward_points_builds_the_reference_pyramid():
+    """forward_points (device k-NN pyramid, int32 global ids, one stacked cloud) == forward on the
+    reference-shaped inputs built by the CPU oracle (int64 batch-relative ids), and the CUDA-graph
+    replay of both equals the eager result bit for bit."""
+    sd, _ = H.state_dict("randlanet_semantickitti.manifest.json", 4)
+    net = M.RandLANetB200(sd)
+    B, N = 3, 4096
+    inp = H.randla_inputs(B, N, 90)
+    want = net(inp).clone()
+    pts = inp["coords"][0].cuda()
+    pyr = net.build_pyramid(pts)
+    for i in range(4):
+        n = inp["coords"][i].shape[1]
+        off = (torch.arange(B).view(B, 1, 1) * n).cuda()
+        assert torch.equal(pyr["neighbor_indices"][i].view(B, n, 16).long(), inp["neighbor_indices"][i].cuda() + off)
+        ns = inp["sub_idx"][i].shape[1]
+        assert torch.equal(pyr["sub_idx"][i].view(B, ns, 16).long(), inp["sub_idx"][i].cuda() + off)
+        offc = (torch.arange(B).view(B, 1, 1) * ns).cuda()
+        assert torch.equal(pyr["interp_idx"][i].view(B, n, 1).long(), inp["interp_idx"][i].cuda() + offc)
+    got = net.forward_points(inp["coords"][0])
+    assert got.shape == want.shape and torch.equal(got, want)
+    g1 = net.forward_points_graphed(pts)
+    g2 = net.forward_points_graphed(pts)
+    assert torch.equal(g1, want) and torch.equal(g2, want)
+    dev_inp = net.to_device(inp)
+    assert torch.equal(net.forward_graphed(dev_inp), want) and torch.equal(net.forward_graphed(dev_inp), want)

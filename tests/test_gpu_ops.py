@@ -195,3 +195,42 @@ def test_search_is_deterministic():
     assert torch.equal(a.neighbors_index, b.neighbors_index) and torch.equal(a.neighbors_distance, b.neighbors_distance)
     c, d = M.fixed_radius_search(P, P, 0.5), M.fixed_radius_search(P, P, 0.5)
     assert torch.equal(c.neighbors_index, d.neighbors_index) and torch.equal(c.neighbors_row_splits, d.neighbors_row_splits)
+
+
+# ------------------------------------------------------------------ grid subsampling (f1)
+@pytest.mark.parametrize("dl,lens", [(0.25, [1200, 0, 1800]), (0.04, [20000]), (1.5, [500, 500])])
+def test_subsample_batch_bit_exact_vs_oracle(dl, lens):
+    import open3d_ml_b200 as M
+    from oracle import ops as O
+    rng = np.random.default_rng(5)
+    n = sum(lens)
+    pts = (rng.random((n, 3)) * [4, 3, 2] - [1, 1, 1]).astype(np.float32)
+    feats = rng.standard_normal((n, 5)).astype(np.float32)
+    labs = rng.integers(0, 6, n).astype(np.int64)
+    got = M.subsample_batch(pts, lens, features=feats, classes=labs, sampleDl=dl)
+    ref = O.c_subsample_batch(pts, lens, feats, labs, dl)
+    assert len(got) == 4 and got[3].dtype == np.int64
+    for g, r in zip(got, ref):
+        assert np.array_equal(np.asarray(g).astype(r.dtype), r)
+    g2 = M.subsample_batch(pts, lens, sampleDl=dl, max_p=9)
+    r2 = O.c_subsample_batch(pts, lens, None, None, dl, max_p=9)
+    assert len(g2) == 2 and np.array_equal(g2[0], r2[0]) and np.array_equal(g2[1], r2[1])
+
+
+def test_subsample_single_cloud_signatures():
+    """The four call shapes of DataProcessing.grid_subsampling (dataprocessing.py:33-49)."""
+    import open3d_ml_b200 as M
+    from oracle import ops as O
+    rng = np.random.default_rng(6)
+    pts = rng.random((5000, 3)).astype(np.float32) * 3
+    feats = rng.random((5000, 3)).astype(np.float32)
+    labs = rng.integers(0, 4, 5000).astype(np.int32)
+    ref = O.c_subsample_batch(pts, [5000], feats, labs, 0.2)
+    p = M.subsample(pts, sampleDl=0.2)
+    assert isinstance(p, np.ndarray) and np.array_equal(p, ref[0])
+    p, f = M.subsample(pts, features=feats, sampleDl=0.2)
+    assert np.array_equal(p, ref[0]) and np.array_equal(f, ref[2])
+    p, l = M.subsample(pts, classes=labs, sampleDl=0.2)
+    assert np.array_equal(l, ref[3])
+    p, f, l = M.subsample(pts, features=feats, classes=labs, sampleDl=0.2)
+    assert np.array_equal(f, ref[2]) and np.array_equal(l, ref[3])

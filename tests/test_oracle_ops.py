@@ -121,3 +121,27 @@ def test_radius_batched_empty():
     i2, r2, _ = O.np_radius(P, P[:50], 0.9, [0, 0, 400], [0, 10, 50])
     assert np.array_equal(r1, r2) and np.array_equal(i1, i2)
     assert np.all(r1[:11] == 0)             # first batch item has no support points
+
+
+def test_subsample_two_restatements_agree_and_partition_the_cloud():
+    """grid subsampling oracle: C (oracle_voxel_reduce) == numpy restatement bit for bit; every point
+    falls in exactly one voxel; barycentres lie inside their voxel; labels are the per-voxel majority."""
+    from oracle import ops as O
+    rng = np.random.default_rng(3)
+    pts = (rng.random((3000, 3)) * [4, 3, 2] - [1, 1, 1]).astype(np.float32)
+    feats = rng.standard_normal((3000, 4)).astype(np.float32)
+    labs = rng.integers(0, 5, 3000).astype(np.int32)
+    lens = [1200, 0, 1800]
+    a = O.c_subsample_batch(pts, lens, feats, labs, 0.25)
+    b = O.np_subsample_batch(pts, lens, feats, labs, 0.25)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    sp, sl, sf, slab = a
+    assert sl.sum() == len(sp) and sl[1] == 0 and len(sp) < 3000
+    origin, _ = O.subsample_range(pts, 0.25)
+    cell = np.floor((sp - origin) / 0.25)
+    assert len(np.unique(np.concatenate([cell[:sl[0]], cell[sl[0]:] + 1000]), axis=0)) == len(sp)
+    only = O.c_subsample_batch(pts, lens, None, None, 0.25)
+    assert len(only) == 2 and np.array_equal(only[0], sp)
+    capped = O.c_subsample_batch(pts, lens, None, None, 0.25, max_p=7)
+    assert list(capped[1]) == [7, 0, 7] and np.array_equal(capped[0][:7], sp[:7])
