@@ -135,6 +135,24 @@ O3DML_API int o3dml_pp_pfn_scatter(const float* points, int point_stride, int po
                          int max_points_per_voxel, float* feat_out, float* canvas,
                          int canvas_nchw, void* stream);
 
+/* ------------------------------------------- detection post-processing ---- */
+
+/* open3d.ml.torch.ops.nms(boxes, scores, nms_overlap_thresh) -- rotated-BEV greedy NMS
+ *   (ml3d/torch/utils/objdet_helper.py:346 <- multiclass_nms <- Anchor3DHead.get_bboxes_single,
+ *   ml3d/torch/models/point_pillars.py:967-1025).  boxes [N,5] = (x0, y0, x1, y1, r): the rectangle
+ *   [x0,x1]x[y0,y1] rotated by r about its centre.  keep_indices int64 [N] receives the kept original
+ *   indices by descending score (ties: lower index first), d_num_keep int64 [1] their count. */
+O3DML_API size_t o3dml_nms_workspace_bytes(int64_t num_boxes);
+O3DML_API int o3dml_nms(const float* boxes, const float* scores, int64_t num_boxes, float iou_threshold,
+                        int64_t* keep_indices, int64_t* d_num_keep, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* open3d.ml.contrib.iou_bev_{cpu,cuda} (mode 0: boxes [.,5] = (x, y, w, h, r)) and iou_3d_{cpu,cuda}
+ *   (mode 1: boxes [.,7] = (x, y, z, w, h, l, ry), ground plane (x, z), vertical span [y - h, y]):
+ *   out [num_a, num_b] float32 IoU (ml3d/metrics/mAP.py:85-89, ml3d/datasets/utils/operations.py:430). */
+O3DML_API int o3dml_iou_matrix(const float* boxes_a, int64_t num_a, const float* boxes_b, int64_t num_b,
+                               int mode, float* out, void* stream);
+
 /* ------------------------------------------------------ dense layers ---- */
 
 /* One operand of the gathered GEMM: rows of `channels` floats (row stride ld); when `index`

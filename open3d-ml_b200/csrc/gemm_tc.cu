@@ -177,6 +177,17 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, W descriptor passed as its two 32-bit words (only the low word varies between MMAs)
+__device__ __forceinline__ void umma_tf32_ts2(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, uint32_t bdesc_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 d;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(bdesc_lo), "r"(bdesc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // registers -> TMEM: 32 lanes x 32 bit, 16 consecutive columns per thread (lane = 32 * (warp % 4) + lane id)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
     asm volatile(
@@ -291,6 +302,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     if (warp == 8) {
         // ================================================================= MMA issuer
         constexpr uint32_t idesc = idesc_tf32(GT_ROWS, BN);
+        // descriptor words (smem_desc_sw128): high = sbo 1024 B | version 1 | SWIZZLE_128B; low = start >> 4 | lbo 1
+        constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t desc_lo0 = (((stage0 + GT_A_BYTES) >> 4) & 0x3fffu) | (1u << 16);
         for (int s = 0; s < nsl; ++s) {
             const int stage = s % S, use = s / S, chunk = s / GT_FLUSH;
 #ifdef O3DML_DEBUG_TIMING
@@ -302,19 +316,19 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             const long long tm1 = clock64();
 #endif
             if (elect_one()) {
-                const uint32_t bh0 = stage0 + (uint32_t)stage * C::STAGE + GT_A_BYTES;
-                const uint32_t bl0 = bh0 + C::B_BYTES;
+                // only the 14-bit start-address field of the W descriptors changes: one add per MMA
+                // (a lone thread retires ~1 dependent instruction per 4-6 cycles; rebuilding the 64-bit
+                // descriptors cost 35-45 cycles per MMA, measured: 414 / 531 cycles to issue 12 MMAs)
+                const uint32_t bh_lo = desc_lo0 + (uint32_t)stage * (C::STAGE >> 4);
+                const uint32_t bl_lo = bh_lo + (C::B_BYTES >> 4);
                 const uint32_t a_hi = tmem + (uint32_t)(C::A_COL0 + stage * 64);
-                const uint32_t a_lo = a_hi + 32;
                 const uint32_t acc = tmem + (uint32_t)((chunk & 1) * BN);
-                const bool first = (s % GT_FLUSH) == 0;
+                const uint32_t first_acc = (s % GT_FLUSH) != 0;
 #pragma unroll
                 for (int ks = 0; ks < GT_KS / 8; ++ks) {        // K = 8 TF32 = 8 TMEM columns / 32 bytes of W per MMA
-                    const uint64_t bh = smem_desc_sw128(bh0 + ks * 32);
-                    const uint64_t bl = smem_desc_sw128(bl0 + ks * 32);
-                    umma_tf32_ts(acc, a_hi + ks * 8, bh, idesc, !(first && ks == 0));
-                    umma_tf32_ts(acc, a_hi + ks * 8, bl, idesc, 1);
-                    umma_tf32_ts(acc, a_lo + ks * 8, bh, idesc, 1);
+                    umma_tf32_ts2(acc, a_hi + ks * 8, bh_lo + ks * 2, DESC_HI, idesc, ks == 0 ? first_acc : 1u);
+                    umma_tf32_ts2(acc, a_hi + ks * 8, bl_lo + ks * 2, DESC_HI, idesc, 1u);
+                    umma_tf32_ts2(acc, a_hi + 32 + ks * 8, bh_lo + ks * 2, DESC_HI, idesc, 1u);
                 }
                 tc::umma_commit(&empty_bar[stage]);
                 if ((s % GT_FLUSH) == GT_FLUSH - 1 || s == nsl - 1) tc::umma_commit(&chunk_bar[chunk & 1]);

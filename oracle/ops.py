@@ -305,3 +305,43 @@ def np_subsample_batch(points, batches_len, features=None, classes=None, sampleD
             ol[v] = vals[np.argmax(cnt)]          # np.unique sorts: first maximum = smallest label
         out.append(ol)
     return tuple(out)
+
+
+# ----------------------------------------------------------------------------
+# rotated IoU / NMS (contract: ops_ref.c, "rotated IoU / NMS")
+# ----------------------------------------------------------------------------
+def c_iou_matrix(a, b, mode):
+    a, b = _f32(a), _f32(b)
+    out = np.zeros((len(a), len(b)), np.float32)
+    if len(a) and len(b):
+        assert lib().oracle_iou_matrix(_p(a, ctypes.c_float), ctypes.c_int64(len(a)), _p(b, ctypes.c_float),
+                                       ctypes.c_int64(len(b)), ctypes.c_int(mode), _p(out, ctypes.c_float)) == 0
+    return out
+
+
+def c_nms(boxes, scores, thr):
+    """-> (keep int64 [K], min |IoU - thr| over the decisive comparisons)."""
+    boxes, scores = _f32(boxes), _f32(scores)
+    keep = np.empty(max(len(boxes), 1), np.int64)
+    gap = ctypes.c_double()
+    L = lib()
+    L.oracle_nms.restype = ctypes.c_int64
+    k = L.oracle_nms(_p(boxes, ctypes.c_float), _p(scores, ctypes.c_float), ctypes.c_int64(len(boxes)),
+                     ctypes.c_float(thr), _p(keep, ctypes.c_int64), ctypes.byref(gap))
+    return keep[:k].copy(), gap.value
+
+
+def np_rbox_area_mc(a, b, samples=400000, seed=0):
+    """Monte-Carlo estimate of the intersection area of two (cx, cy, w, h, r) boxes: an independent check."""
+    rng = np.random.default_rng(seed)
+    r = max(a[2], a[3], b[2], b[3])
+    lo = np.minimum(a[:2], b[:2]) - r
+    hi = np.maximum(a[:2], b[:2]) + r
+    p = rng.random((samples, 2)) * (hi - lo) + lo
+
+    def inside(bx):
+        c, s = np.cos(bx[4]), np.sin(bx[4])
+        d = p - bx[:2]
+        u, v = d[:, 0] * c + d[:, 1] * s, -d[:, 0] * s + d[:, 1] * c
+        return (np.abs(u) <= bx[2] / 2) & (np.abs(v) <= bx[3] / 2)
+    return float(np.mean(inside(a) & inside(b)) * np.prod(hi - lo))

@@ -276,3 +276,117 @@ EXPORT int oracle_voxel_reduce(const float *points, int point_stride, const floa
     }
     return 0;
 }
+
+/* ------------------------------------------------------ rotated IoU / NMS ---- */
+/* Restates the contract of open3d.ml.torch.ops.nms / contrib.iou_bev / iou_3d as consumed at
+ * ml3d/torch/utils/objdet_helper.py:316-350 and ml3d/metrics/mAP.py:85-89 (PARITY UNPINNED: upstream
+ * Open3D is absent).  Double precision, Sutherland-Hodgman clipping. */
+typedef struct { double cx, cy, w, h, c, s; } rbox_t;
+
+static rbox_t rbox_make(double cx, double cy, double w, double h, double r) {
+    rbox_t b = {cx, cy, w, h, cos(r), sin(r)};
+    return b;
+}
+static void rbox_corners(const rbox_t *b, double *x, double *y) {
+    const double hw = 0.5 * b->w, hh = 0.5 * b->h;
+    const double dx[4] = {-hw, hw, hw, -hw}, dy[4] = {-hh, -hh, hh, hh};
+    for (int i = 0; i < 4; ++i) {
+        x[i] = b->cx + dx[i] * b->c - dy[i] * b->s;
+        y[i] = b->cy + dx[i] * b->s + dy[i] * b->c;
+    }
+}
+static double rbox_intersection(const rbox_t *a, const rbox_t *b) {
+    if (!(a->w > 0) || !(a->h > 0) || !(b->w > 0) || !(b->h > 0)) return 0.0;
+    double px[16], py[16], qx[16], qy[16], bx[4], by[4];
+    int n = 4;
+    rbox_corners(a, px, py);
+    rbox_corners(b, bx, by);
+    for (int e = 0; e < 4 && n > 0; ++e) {
+        double x0 = bx[e], y0 = by[e], ex = bx[(e + 1) & 3] - x0, ey = by[(e + 1) & 3] - y0;
+        int m = 0;
+        double sx = px[n - 1], sy = py[n - 1];
+        double sd = ex * (sy - y0) - ey * (sx - x0);
+        for (int i = 0; i < n; ++i) {
+            double tx = px[i], ty = py[i];
+            double td = ex * (ty - y0) - ey * (tx - x0);
+            if ((sd >= 0) != (td >= 0)) {
+                double t = sd / (sd - td);
+                qx[m] = sx + t * (tx - sx); qy[m] = sy + t * (ty - sy); ++m;
+            }
+            if (td >= 0) { qx[m] = tx; qy[m] = ty; ++m; }
+            sx = tx; sy = ty; sd = td;
+        }
+        n = m;
+        for (int i = 0; i < n; ++i) { px[i] = qx[i]; py[i] = qy[i]; }
+    }
+    if (n < 3) return 0.0;
+    double area = 0;
+    for (int i = 0; i < n; ++i) {
+        int j = (i + 1 == n) ? 0 : i + 1;
+        area += px[i] * py[j] - px[j] * py[i];
+    }
+    return area > 0 ? 0.5 * area : 0.0;
+}
+static double rbox_iou(const rbox_t *a, const rbox_t *b) {
+    double inter = rbox_intersection(a, b);
+    double uni = a->w * a->h + b->w * b->h - inter;
+    return uni > 0 ? inter / uni : 0.0;
+}
+
+/* mode 0: [.,5] (x, y, w, h, r); mode 1: [.,7] (x, y, z, w, h, l, ry) */
+EXPORT int oracle_iou_matrix(const float *a, int64_t na, const float *b, int64_t nb, int mode, float *out) {
+    for (int64_t i = 0; i < na; ++i)
+        for (int64_t j = 0; j < nb; ++j) {
+            if (mode == 0) {
+                const float *p = a + 5 * i, *q = b + 5 * j;
+                rbox_t ra = rbox_make(p[0], p[1], p[2], p[3], p[4]), rb = rbox_make(q[0], q[1], q[2], q[3], q[4]);
+                out[i * nb + j] = (float)rbox_iou(&ra, &rb);
+            } else {
+                const float *p = a + 7 * i, *q = b + 7 * j;
+                rbox_t ra = rbox_make(p[0], p[2], p[3], p[5], p[6]), rb = rbox_make(q[0], q[2], q[3], q[5], q[6]);
+                double inter2 = rbox_intersection(&ra, &rb);
+                double ymax = p[1] < q[1] ? p[1] : q[1];
+                double ya = (double)p[1] - p[4], yb = (double)q[1] - q[4];
+                double ymin = ya > yb ? ya : yb;
+                double ih = ymax - ymin > 0 ? ymax - ymin : 0;
+                double inter = inter2 * ih;
+                double uni = (double)p[3] * p[4] * p[5] + (double)q[3] * q[4] * q[5] - inter;
+                out[i * nb + j] = (float)(uni > 0 ? inter / uni : 0.0);
+            }
+        }
+    return 0;
+}
+
+/* boxes [N,5] (x0, y0, x1, y1, r); visiting order = descending score, ties lower index first.
+ * margin > 0 additionally reports (via *min_gap) how close any decisive IoU came to thr. */
+EXPORT int64_t oracle_nms(const float *boxes, const float *scores, int64_t n, float thr, int64_t *keep,
+                          double *min_gap) {
+    int64_t *order = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; ++i) order[i] = i;
+    for (int64_t i = 1; i < n; ++i) { /* stable insertion sort, descending score */
+        int64_t v = order[i], j = i;
+        while (j > 0 && scores[order[j - 1]] < scores[v]) { order[j] = order[j - 1]; --j; }
+        order[j] = v;
+    }
+    int64_t kept = 0;
+    double gap = 1e30;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *p = boxes + 5 * order[i];
+        rbox_t a = rbox_make(0.5 * ((double)p[0] + p[2]), 0.5 * ((double)p[1] + p[3]), (double)p[2] - p[0],
+                             (double)p[3] - p[1], p[4]);
+        int dead = 0;
+        for (int64_t k = 0; k < kept && !dead; ++k) {
+            const float *q = boxes + 5 * keep[k];
+            rbox_t b = rbox_make(0.5 * ((double)q[0] + q[2]), 0.5 * ((double)q[1] + q[3]), (double)q[2] - q[0],
+                                 (double)q[3] - q[1], q[4]);
+            double iou = rbox_iou(&a, &b);
+            double g = fabs(iou - (double)thr);
+            if (g < gap) gap = g;
+            if (iou > thr) dead = 1;
+        }
+        if (!dead) keep[kept++] = order[i];
+    }
+    if (min_gap) *min_gap = gap;
+    free(order);
+    return kept;
+}

@@ -145,3 +145,39 @@ def test_subsample_two_restatements_agree_and_partition_the_cloud():
     assert len(only) == 2 and np.array_equal(only[0], sp)
     capped = O.c_subsample_batch(pts, lens, None, None, 0.25, max_p=7)
     assert list(capped[1]) == [7, 0, 7] and np.array_equal(capped[0][:7], sp[:7])
+
+
+def test_rotated_iou_oracle_known_answers():
+    from oracle import ops as O
+    a = np.array([[0, 0, 2, 2, 0.0]], np.float32)
+    assert abs(O.c_iou_matrix(a, a, 0)[0, 0] - 1) < 1e-6
+    b = np.array([[1, 0, 2, 2, 0.0], [0, 0, 2, 2, np.pi / 4], [5, 5, 1, 1, 0.3], [0, 0, 4, 1, np.pi / 2]], np.float32)
+    m = O.c_iou_matrix(a, b, 0)[0]
+    assert abs(m[0] - 2 / 6) < 1e-6                                   # half overlap: 2 / (4 + 4 - 2)
+    oct_area = 8 * (np.sqrt(2) - 1)                                   # square x square rotated 45 deg = octagon
+    assert abs(m[1] - oct_area / (8 - oct_area)) < 1e-6 and m[2] == 0
+    assert abs(m[3] - 2 / 6) < 1e-6                                   # 1 x 4 upright strip crosses the square: 2
+    assert np.allclose(O.c_iou_matrix(b, a, 0)[:, 0], m)              # symmetric
+    rng = np.random.default_rng(1)
+    for _ in range(4):
+        p = np.concatenate([rng.random(2) * 2, rng.random(2) * 3 + 0.5, rng.random(1) * 6]).astype(np.float32)
+        q = np.concatenate([rng.random(2) * 2, rng.random(2) * 3 + 0.5, rng.random(1) * 6]).astype(np.float32)
+        iou = O.c_iou_matrix(p[None], q[None], 0)[0, 0]
+        inter = iou * (p[2] * p[3] + q[2] * q[3]) / (1 + iou)
+        assert abs(inter - O.np_rbox_area_mc(p.astype(np.float64), q.astype(np.float64))) < 0.05
+    # 3-D: same footprint, half the height overlaps
+    c = np.array([[0, 2, 0, 2, 2, 2, 0.0]], np.float32)
+    d = np.array([[0, 1, 0, 2, 2, 2, 0.0]], np.float32)
+    assert abs(O.c_iou_matrix(c, d, 1)[0, 0] - 4 / 12) < 1e-6
+
+
+def test_nms_oracle_is_greedy_by_score():
+    from oracle import ops as O
+    boxes = np.array([[0, 0, 2, 2, 0], [0.1, 0, 2.1, 2, 0], [5, 5, 6, 6, 0.5], [0, 0, 2, 2, 0.05], [5, 5, 6, 6, 0.5]],
+                     np.float32)
+    scores = np.array([0.5, 0.9, 0.3, 0.8, 0.3], np.float32)
+    keep, _ = O.c_nms(boxes, scores, 0.5)
+    assert list(keep) == [1, 2]                                       # 3 and 0 overlap 1; 4 duplicates 2 (tie: 2 first)
+    keep, _ = O.c_nms(boxes, scores, 0.99)
+    assert list(keep) == [1, 3, 0, 2]
+    assert len(O.c_nms(boxes[:0], scores[:0], 0.5)[0]) == 0

@@ -24,6 +24,8 @@ def run(name, fn, nsl):
     cyc = a[4003] - t0
     print("%-26s %6.1f us/launch | CTA0 %6d cycles | per slice: %5.0f cycles" % (
         name, ev[0].elapsed_time(ev[1]) * 10, cyc, (a[4002] - t0) / nsl))
+    print("   CTA 0 phases       : prologue (start -> first slice landed) %6d | main loop %7d | epilogue (last chunk done -> exit) %6d cycles" % (
+        a[1] - t0, a[4002] - a[1], a[4003] - a[4002]))
     k = slice(2, n - 1)
     print("   converter thread 0: wait_full %6.0f  split+fence %6.0f   (cycles, mean over slices)" % (
         (sl[k, 1] - sl[k, 0]).mean(), (sl[k, 2] - sl[k, 1]).mean()))
