@@ -9,7 +9,8 @@ __version__ = "0.1.0"
 
 from . import ops, synth, shard  # noqa: F401,E402
 from .ops import (voxelize, ragged_to_dense, knn_search, fixed_radius_search,  # noqa: F401,E402
-                  FixedRadiusSearch, KNNSearch, NearestNeighborSearch, subsample, subsample_batch)
+                  FixedRadiusSearch, KNNSearch, NearestNeighborSearch, subsample, subsample_batch,
+                  nms, iou_bev, iou_3d)
 
 
 def __getattr__(name):

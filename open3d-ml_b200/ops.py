@@ -323,3 +323,47 @@ def subsample(points, features=None, classes=None, sampleDl=0.1, verbose=0):
     r = subsample_batch(points, [len(points)], features, classes, sampleDl)
     out = (r[0],) + tuple(r[2:])
     return out[0] if len(out) == 1 else out
+
+
+# ------------------------------------------------------------------ detection post-processing
+def nms(boxes, scores, nms_overlap_thresh):
+    """open3d.ml.torch.ops.nms (ml3d/torch/utils/objdet_helper.py:346): boxes [N,5] = (x0, y0, x1, y1, r),
+    scores [N] -> int64 indices of the kept boxes by descending score.  One device->host read (the count)."""
+    if boxes.dim() != 2 or boxes.shape[1] != 5:
+        raise RuntimeError("nms: boxes must have shape [N,5], got %s" % (tuple(boxes.shape),))
+    if scores.dim() != 1 or scores.shape[0] != boxes.shape[0]:
+        raise RuntimeError("nms: scores must have shape [N]")
+    was_cuda = boxes.is_cuda
+    b = _dev(boxes).to(torch.float32).contiguous()
+    s = _dev(scores).to(torch.float32).contiguous()
+    n = b.shape[0]
+    keep = torch.empty((n,), dtype=torch.int64, device=b.device)
+    cnt = torch.zeros((1,), dtype=torch.int64, device=b.device)
+    wsb = L.lib().o3dml_nms_workspace_bytes(n)
+    ws = torch.empty((wsb,), dtype=torch.uint8, device=b.device)
+    L.check(L.lib().o3dml_nms(L.ptr(b), L.ptr(s), n, float(nms_overlap_thresh), L.ptr(keep), L.ptr(cnt), L.ptr(ws),
+                              wsb, L.stream()))
+    out = keep[:int(cnt.item())]
+    return out if was_cuda else out.cpu()
+
+
+def _iou(a, b, mode, width):
+    a_np, b_np = isinstance(a, np.ndarray), isinstance(b, np.ndarray)
+    ta = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)) if a_np else a
+    tb = torch.as_tensor(np.ascontiguousarray(b, dtype=np.float32)) if b_np else b
+    if ta.dim() != 2 or tb.dim() != 2 or ta.shape[1] != width or tb.shape[1] != width:
+        raise RuntimeError("iou: boxes must have shape [N,%d]" % width)
+    ta, tb = _dev(ta).to(torch.float32).contiguous(), _dev(tb).to(torch.float32).contiguous()
+    out = torch.zeros((ta.shape[0], tb.shape[0]), dtype=torch.float32, device=ta.device)
+    L.check(L.lib().o3dml_iou_matrix(L.ptr(ta), ta.shape[0], L.ptr(tb), tb.shape[0], mode, L.ptr(out), L.stream()))
+    return out.cpu().numpy() if a_np else out
+
+
+def iou_bev(boxes_a, boxes_b):
+    """open3d.ml.contrib.iou_bev_{cpu,cuda} (ml3d/metrics/mAP.py:85): [N,5] x [M,5] (x, y, w, h, r) -> [N,M]."""
+    return _iou(boxes_a, boxes_b, 0, 5)
+
+
+def iou_3d(boxes_a, boxes_b):
+    """open3d.ml.contrib.iou_3d_{cpu,cuda} (ml3d/metrics/mAP.py:88): [N,7] x [M,7] (x, y, z, w, h, l, ry)."""
+    return _iou(boxes_a, boxes_b, 1, 7)

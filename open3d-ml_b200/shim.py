@@ -103,7 +103,7 @@ def install(ml3d_root=None):
     mlt = _module("open3d.ml.torch")
     _module("open3d.ml.torch.ops", voxelize=O.voxelize, ragged_to_dense=O.ragged_to_dense,
             knn_search=O.knn_search, fixed_radius_search=O.fixed_radius_search,
-            nms=_not_on_hot_path("ops.nms"),
+            nms=O.nms,
             reduce_subarrays_sum=_not_on_hot_path("ops.reduce_subarrays_sum"),
             voxel_pooling=_not_on_hot_path("ops.voxel_pooling"),
             continuous_conv=_not_on_hot_path("ops.continuous_conv"),
@@ -113,8 +113,7 @@ def install(ml3d_root=None):
     _module("open3d.ml.torch.layers", FixedRadiusSearch=O.FixedRadiusSearch, KNNSearch=O.KNNSearch,
             SparseConv=stub_layer, SparseConvTranspose=stub_layer)
     _module("open3d.ml.contrib", subsample=O.subsample, subsample_batch=O.subsample_batch,
-            **{n: _not_on_hot_path("contrib." + n)
-               for n in ("iou_bev_cpu", "iou_3d_cpu", "iou_bev_cuda", "iou_3d_cuda")})
+            iou_bev_cpu=O.iou_bev, iou_bev_cuda=O.iou_bev, iou_3d_cpu=O.iou_3d, iou_3d_cuda=O.iou_3d)
     vis = _module("open3d.visualization")
     tb = _module("open3d.visualization.tensorboard_plugin")
     _module("open3d.visualization.tensorboard_plugin.summary")

@@ -234,3 +234,56 @@ def test_subsample_single_cloud_signatures():
     assert np.array_equal(l, ref[3])
     p, f, l = M.subsample(pts, features=feats, classes=labs, sampleDl=0.2)
     assert np.array_equal(f, ref[2]) and np.array_equal(l, ref[3])
+
+
+# ------------------------------------------------------------------ rotated IoU / NMS (f2)
+def _rand_boxes(n, seed, spread=20.0):
+    rng = np.random.default_rng(seed)
+    c = rng.random((n, 2)) * spread
+    wh = rng.random((n, 2)) * 3 + 0.5
+    r = (rng.random((n, 1)) - 0.5) * 2 * np.pi
+    return np.concatenate([c, wh, r], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("na,nb", [(1, 1), (37, 53), (300, 200)])
+def test_iou_bev_and_3d_vs_oracle(na, nb):
+    import open3d_ml_b200 as M
+    from oracle import ops as O
+    a, b = _rand_boxes(na, 1, 8.0), _rand_boxes(nb, 2, 8.0)
+    got = M.iou_bev(a, b)
+    assert isinstance(got, np.ndarray) and np.abs(got - O.c_iou_matrix(a, b, 0)).max() < 2e-5
+    rng = np.random.default_rng(3)
+    def to3d(x, seed):
+        y = rng.random((len(x), 1)) * 2
+        h = rng.random((len(x), 1)) * 2 + 0.5
+        return np.concatenate([x[:, :1], y, x[:, 1:2], x[:, 2:3], h, x[:, 3:4], x[:, 4:5]], 1).astype(np.float32)
+    a3, b3 = to3d(a, 4), to3d(b, 5)
+    got3 = M.iou_3d(torch.from_numpy(a3).cuda(), torch.from_numpy(b3).cuda())
+    assert got3.is_cuda and np.abs(got3.cpu().numpy() - O.c_iou_matrix(a3, b3, 1)).max() < 2e-5
+    assert M.iou_bev(a[:0], b).shape == (0, nb)
+
+
+@pytest.mark.parametrize("n,thr,spread", [(1, 0.5, 5.0), (100, 0.01, 20.0), (1000, 0.32, 30.0), (4097, 0.5, 60.0), (513, 0.01, 3.0)])
+def test_nms_vs_oracle(n, thr, spread):
+    """Kept indices equal the oracle's whenever no decisive IoU lies within fp32 noise of the threshold
+    (the oracle reports the closest approach; the seeds here keep it above 1e-5)."""
+    import open3d_ml_b200 as M
+    from oracle import ops as O
+    bx = _rand_boxes(n, 7 + n, spread)
+    boxes = np.stack([bx[:, 0] - bx[:, 2] / 2, bx[:, 1] - bx[:, 3] / 2, bx[:, 0] + bx[:, 2] / 2, bx[:, 1] + bx[:, 3] / 2,
+                      bx[:, 4]], 1).astype(np.float32)
+    scores = np.random.default_rng(n).random(n).astype(np.float32)
+    scores[n // 2:] = scores[:n - n // 2]                    # exact ties: lower index first
+    ref, gap = O.c_nms(boxes, scores, thr)
+    assert gap > 1e-5 or n == 1
+    got = M.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), thr)
+    assert got.dtype == torch.int64 and got.is_cuda and np.array_equal(got.cpu().numpy(), ref)
+    got_cpu = M.nms(torch.from_numpy(boxes), torch.from_numpy(scores), thr)
+    assert not got_cpu.is_cuda and np.array_equal(got_cpu.numpy(), ref)
+
+
+def test_nms_empty_and_bad_shapes():
+    import open3d_ml_b200 as M
+    assert M.nms(torch.zeros(0, 5).cuda(), torch.zeros(0).cuda(), 0.5).numel() == 0
+    with pytest.raises(RuntimeError):
+        M.nms(torch.zeros(4, 4).cuda(), torch.zeros(4).cuda(), 0.5)
