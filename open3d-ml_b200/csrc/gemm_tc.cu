@@ -208,7 +208,7 @@ struct GtCfg {
     static constexpr int TMEM_COLS = 512;                          // 2 * BN + STAGES * 64 <= 512, power of two
     static_assert(2 * BN + STAGES * 64 <= 512, "TMEM budget");
     static_assert(STAGES <= GT_FLUSH + 1, "a chunk must be folded before its TMEM buffer is reused");
-    static constexpr int TAIL = GT_MAX_SRC * GT_ROWS * 8 + GT_ROWS * 8 + 256;
+    static constexpr int TAIL = GT_MAX_SRC * GT_ROWS * 8 + GT_ROWS * 8 + 2 * BN * 4 + 256;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE + TAIL + 1024;
 };
 
@@ -233,7 +233,9 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
     uint8_t* stages = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);           // 1024-byte aligned
     const float** rowptr = reinterpret_cast<const float**>(stages + S * C::STAGE);   // [src][row]
     int64_t* rown = reinterpret_cast<int64_t*>(rowptr + GT_MAX_SRC * GT_ROWS);       // [row] output row or -1
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(rown + GT_ROWS);
+    float* s_scale = reinterpret_cast<float*>(rown + GT_ROWS);                       // [BN] folded BN scale of this column tile
+    float* s_shift = s_scale + BN;                                                   // [BN]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(s_shift + BN);
     uint64_t* full_bar = mbar;                // [S] operands of the slice landed
     uint64_t* conv_bar = mbar + S;            // [S] A tile split + fenced
     uint64_t* empty_bar = mbar + 2 * S;       // [S] MMAs that read the stage are done
@@ -269,6 +271,11 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             n = (oy < p.OH && ox < p.OW) ? ((int64_t)cb * p.OH + oy) * p.OW + ox : -1;
         }
         rown[m] = n;
+    }
+    for (int i = tid; i < BN; i += blockDim.x) {      // per-column epilogue constants: read once, not per element
+        const int c = col0 + i;
+        s_scale[i] = (p.scale && c < p.Cout) ? p.scale[c] : 1.f;
+        s_shift[i] = (p.shift && c < p.Cout) ? p.shift[c] : 0.f;
     }
     if (GATHER) {
         for (int i = tid; i < p.nsrc * GT_ROWS; i += blockDim.x) {
@@ -492,15 +499,16 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                 tc::tmem_ld16(tmem_lane + (last_chunk & 1) * BN + c0, v);   // warp-collective
                 const int cbase = col0 + c0;
                 if (n < 0 || cbase >= p.Cout) continue;
+                // staged outputs get the residual and the activation in the row-coalesced copy-out below
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int c = cbase + j;
-                    if (c < p.Cout) {
-                        float x = v[j] + racc[q * 16 + j];
-                        x = fmaf(x, p.scale ? p.scale[c] : 1.f, p.shift ? p.shift[c] : 0.f);
-                        if (p.residual) x += p.residual[(size_t)n * p.res_ld + c];
-                        v[j] = apply_act(x, p.act, p.slope);
+                    float x = fmaf(v[j] + racc[q * 16 + j], s_scale[c0 + j], s_shift[c0 + j]);
+                    if (!staged) {
+                        const int c = cbase + j;
+                        if (p.residual && c < p.Cout) x += p.residual[(size_t)n * p.res_ld + c];
+                        x = apply_act(x, p.act, p.slope);
                     }
+                    v[j] = x;
                 }
                 if (staged) {
 #pragma unroll
@@ -541,7 +549,21 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
                 for (int r = tid / LPR; r < GT_ROWS; r += GT_CONV_THREADS / LPR) {
                     const int64_t nr = rown[r];
                     if (nr < 0) continue;
-                    const float4 v = *reinterpret_cast<const float4*>(stg + r * SLD + c);
+                    float4 v = *reinterpret_cast<const float4*>(stg + r * SLD + c);
+                    if (p.residual) {
+                        const float* rp = p.residual + (size_t)nr * p.res_ld + cg;
+                        if (cg + 3 < p.Cout && (p.res_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) {
+                            const float4 rv = *reinterpret_cast<const float4*>(rp);
+                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                        } else {
+                            if (cg < p.Cout) v.x += rp[0];
+                            if (cg + 1 < p.Cout) v.y += rp[1];
+                            if (cg + 2 < p.Cout) v.z += rp[2];
+                            if (cg + 3 < p.Cout) v.w += rp[3];
+                        }
+                    }
+                    v.x = apply_act(v.x, p.act, p.slope); v.y = apply_act(v.y, p.act, p.slope);
+                    v.z = apply_act(v.z, p.act, p.slope); v.w = apply_act(v.w, p.act, p.slope);
                     float* o;
                     if (p.out_mode == 0) {
                         o = p.out + (size_t)nr * p.out_ld + cg;

@@ -49,6 +49,8 @@ def _plan(cfg):
             concats.append(bi)
         dec.append(dict(kind=blk, in_dim=in_dim, out_dim=out_dim, layer=layer))
         in_dim = out_dim
+        if bi == 0 and cfg.get("reduce_fc", False):       # kpconv.py:219-220
+            out_dim //= 2
         if "upsample" in blk:
             layer -= 1
             r *= 0.5
@@ -106,7 +108,9 @@ class KPFCNNB200:
         for bi, b in enumerate(self.dec):
             if b["kind"] == "unary":
                 unary("decoder_blocks.%d" % bi, self.use_bn)
-        unary("head_mlp", False)
+        # kpconv.py:228-249: reduce_fc -> head_mlp with BN, head_softmax without activation
+        self.reduce_fc = bool(cfg.get("reduce_fc", False))
+        unary("head_mlp", self.reduce_fc and self.use_bn)
         unary("head_softmax", False)
         self.num_classes = sd["head_softmax.mlp.weight"].shape[0]
 
@@ -197,7 +201,7 @@ class KPFCNNB200:
         if pending is not None:
             raise RuntimeError("KPFCNNB200: dangling upsample block")
         x = self._lin("head_mlp", [L.make_src(x)], x.shape[0], "leaky")
-        return self._lin("head_softmax", [L.make_src(x)], x.shape[0], "leaky")
+        return self._lin("head_softmax", [L.make_src(x)], x.shape[0], None if self.reduce_fc else "leaky")
 
     __call__ = forward
 

@@ -152,8 +152,11 @@ def _populate(m):
 
         def _todo(*a, **k):
             raise NotImplementedError("not on the hot path (SURVEY.md 2.2)")
-        m.voxelize, m.ragged_to_dense = voxelize, ragged_to_dense
-        m.nms = m.knn_search = m.reduce_subarrays_sum = _todo
+        def nms(boxes, scores, thr):
+            keep, _ = O.c_nms(boxes.detach().cpu().numpy(), scores.detach().cpu().numpy(), float(thr))
+            return torch.from_numpy(keep).to(boxes.device)
+        m.voxelize, m.ragged_to_dense, m.nms = voxelize, ragged_to_dense, nms
+        m.knn_search = m.reduce_subarrays_sum = _todo
     elif name == "open3d.ml.torch.layers":
         R = collections.namedtuple("FixedRadiusSearchResult",
                                    "neighbors_index neighbors_row_splits neighbors_distance")
@@ -170,9 +173,20 @@ def _populate(m):
     elif name == "open3d.ml.contrib":
         def _todo(*a, **k):
             raise NotImplementedError("not on the hot path (SURVEY.md 2.2)")
-        for n in ("subsample", "subsample_batch", "iou_bev_cpu", "iou_3d_cpu", "iou_bev_cuda",
-                  "iou_3d_cuda"):
-            setattr(m, n, _todo)
+        def subsample_batch(points, batches_len, features=None, classes=None, sampleDl=0.1,
+                            method="barycenter", max_p=0, verbose=0):
+            r = O.c_subsample_batch(points, batches_len, features, classes, sampleDl, max_p)
+            if classes is not None:
+                r = r[:-1] + (r[-1].astype(np.asarray(classes).dtype),)
+            return r
+
+        def subsample(points, features=None, classes=None, sampleDl=0.1, verbose=0):
+            r = subsample_batch(points, [len(points)], features, classes, sampleDl)
+            out = (r[0],) + tuple(r[2:])
+            return out[0] if len(out) == 1 else out
+        m.subsample, m.subsample_batch = subsample, subsample_batch
+        m.iou_bev_cpu = m.iou_bev_cuda = lambda a, b: O.c_iou_matrix(a, b, 0)
+        m.iou_3d_cpu = m.iou_3d_cuda = lambda a, b: O.c_iou_matrix(a, b, 1)
     elif name == "open3d.visualization.tensorboard_plugin":
         m.summary = types.ModuleType(name + ".summary")
     elif name in ("matplotlib.pyplot", "matplotlib.cm", "matplotlib"):

@@ -105,3 +105,16 @@ def test_pipelined_runner_tree_helpers_and_cpu_refusal():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError):
             P.PipelinedRunner(lambda x: x)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="/root/reference absent (GPU box)")
+def test_reference_boundary_script_dry_run_with_oracle_ops():
+    """tests/ref_boundary_cases.py (the script behind the -m gpu boundary tests) on this CPU box with the oracle
+    bound instead of the CUDA library: the unmodified RandLANet preprocess / transform / forward flow works."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_boundary_cases.py"),
+                        "randlanet_patch", "--ops", "oracle"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert res["ops"] == "oracle" and res["ref_shape"] == [1, 8192, 19]
