@@ -599,8 +599,9 @@ extern "C" int o3dml_randla_lfa_pool(int stage, int d, const float* coords, cons
         LFA_CASE(64)
         LFA_CASE(128)
         LFA_CASE(256)
+        LFA_CASE(512)   // the 5-level configs (s3dis / semantic3d / toronto3d / parislille3d: dim_output [16,64,128,256,512])
         default:
-            O3DML_FAIL(O3DML_ERR_UNSUPPORTED, "lfa: d_out %d not in {16,32,64,128,256}", d);
+            O3DML_FAIL(O3DML_ERR_UNSUPPORTED, "lfa: d_out %d not in {16,32,64,128,256,512}", d);
     }
 #undef LFA_CASE
 }

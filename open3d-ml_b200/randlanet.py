@@ -21,8 +21,10 @@ from . import _lib as L
 
 BN_EPS = 1e-6  # randlanet.py:77,499
 # d_out values served by the tcgen05 kernel (lfa_tc.cu).  d = 16 stays on the FP32 SIMT kernel: its
-# 16x16 score product is too small to pay for the per-tile MMA round trip (0.84 vs 1.23 ms measured).
+# 16x16 score product is too small to pay for the per-tile MMA round trip (0.84 vs 1.23 ms measured);
+# d = 512 (fifth encoder of the 5-level configs, a few hundred points) runs on the tiled SIMT kernel (lfa.cu).
 TC_DIMS = (32, 64, 128, 256)
+SUPPORTED_DIMS = (16, 32, 64, 128, 256, 512)
 
 
 def _fold_bn(sd, prefix, bias=None, eps=BN_EPS):
@@ -83,6 +85,9 @@ class RandLANetB200:
                 put("%s.%s.score.wt" % (p, pool), sd["%s.%s.score_fn.0.weight" % (p, pool)].t())
                 put("%s.%s.score.b" % (p, pool), sd["%s.%s.score_fn.0.bias" % (p, pool)])
             d = sd[p + ".pool2.mlp.conv.weight"].shape[0]
+            if d not in SUPPORTED_DIMS:
+                raise RuntimeError("RandLANetB200: encoder %d has dim_output %d; the fused LFA kernels serve %s"
+                                   % (i, d, SUPPORTED_DIMS))
             self.d_out.append(d)
             if d in TC_DIMS:   # tcgen05 path: host-packed fp16 hi/lo operand images ([out][in])
                 for pool in ("pool1", "pool2"):

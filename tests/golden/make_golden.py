@@ -76,6 +76,38 @@ def make_randlanet():
     np.savez_compressed(os.path.join(HERE, "randlanet_small.npz"), **save)
 
 
+def make_randlanet_s3dis():
+    """5-level config (dim_output [16, 64, 128, 256, 512], ratios [4, 4, 4, 4, 2], 6 input channels):
+    manifest + a small golden forward of the unmodified class."""
+    from ml3d.torch.models import RandLANet
+    cfg = refshim.load_cfg("randlanet_s3dis.yml")
+    net = RandLANet(**cfg.model)
+    net.device = "cpu"
+    net.eval()
+    man = weights.manifest_from_state_dict(net.state_dict())
+    ratios = list(cfg.model["sub_sampling_ratio"])
+    weights.save_manifest(os.path.join(HERE, "randlanet_s3dis.manifest.json"), man,
+                          dict(source="ml3d/configs/randlanet_s3dis.yml",
+                               cfg=dict(num_layers=int(cfg.model["num_layers"]), sub_sampling_ratio=ratios,
+                                        in_channels=int(cfg.model["in_channels"]))))
+    sd = weights.seeded_state_dict(man, SEED)
+    net.load_state_dict(sd, strict=True)
+    B, N = 2, 8192
+    per = [MT.randlanet_build_inputs(synth.semantickitti_cloud(N, 300 + b), num_layers=5, ratios=ratios) for b in range(B)]
+    inp = {k: [torch.from_numpy(np.stack([q[k][i] for q in per])) for i in range(5)]
+           for k in ("coords", "neighbor_indices", "sub_idx", "interp_idx")}
+    rng = np.random.default_rng(7)
+    inp["features"] = torch.cat([inp["coords"][0], torch.from_numpy(rng.random((B, N, 3)).astype(np.float32))], -1)
+    with torch.no_grad():
+        out = net(inp)
+        port = MT.randlanet_forward(sd, inp, num_layers=5)
+    err = (port - out).abs().max().item() / out.abs().max().item()
+    print("randlanet_s3dis: port vs reference rel err %.3e" % err)
+    assert err < 1e-5
+    np.savez_compressed(os.path.join(HERE, "randlanet_s3dis_small.npz"), logits=out.numpy(), B=B, N=N, seed0=300,
+                        weight_seed=SEED, extra_feat=inp["features"][..., 3:].numpy())
+
+
 # ------------------------------------------------------------------ PointPillars
 PP_SMALL = dict(point_cloud_range=[0, -10.24, -3, 20.48, 10.24, 1], output_shape=[128, 128])
 
@@ -253,6 +285,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["randlanet", "pointpillars", "kpconv"]
     if "randlanet" in which:
         make_randlanet()
+    if "randlanet_s3dis" in which:
+        make_randlanet_s3dis()
     if "pointpillars" in which:
         make_pointpillars()
     if "kpconv" in which:

@@ -114,3 +114,20 @@ def test_lfa16_rejects_device_weights():
     assert rc != 0
     with pytest.raises(RuntimeError):
         L.check(rc)
+
+
+@pytest.mark.parametrize("stage", [1, 2])
+def test_lfa_simt_d512_vs_float64_reference(stage):
+    """d_out = 512 (fifth encoder of the s3dis / semantic3d / toronto3d / parislille3d configs,
+    randlanet_s3dis.yml: dim_output [16, 64, 128, 256, 512]) runs on the FP32 SIMT kernel."""
+    d, B, N = 512, 2, 150
+    args = make(d, B, N, 900 + stage)
+    coords, nidx, feat, w10, s10, t10, wl2, s2, t2, ws, bs = args
+    want = lfa_reference(stage, d, *args, B, N)
+    wl2t, wst = wl2.t().contiguous().cuda(), ws.t().contiguous().cuda()
+    o = torch.full((B * N, d), float("nan")).cuda()
+    L.check(L.lib().o3dml_randla_lfa_pool(stage, d, L.ptr(coords), L.ptr(nidx), 1, 16, L.ptr(feat), B, N,
+                                          L.ptr(w10), L.ptr(s10), L.ptr(t10), L.ptr(wl2t), L.ptr(s2), L.ptr(t2),
+                                          L.ptr(wst), L.ptr(bs), L.ptr(o), L.stream()))
+    torch.cuda.synchronize()
+    assert rel_err(o.cpu().double(), want) < 1e-4

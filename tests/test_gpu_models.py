@@ -244,3 +244,24 @@ def test_randlanet_forward_points_builds_the_reference_pyramid():
     assert torch.equal(g1, want) and torch.equal(g2, want)
     dev_inp = net.to_device(inp)
     assert torch.equal(net.forward_graphed(dev_inp), want) and torch.equal(net.forward_graphed(dev_inp), want)
+
+
+def test_randlanet_five_level_config_vs_golden_reference():
+    """randlanet_s3dis.yml (also semantic3d / toronto3d / parislille3d): 5 encoders, d_out up to 512, ratios
+    [4, 4, 4, 4, 2], 6 input channels -- golden logits of the unmodified reference class."""
+    g = H.golden("randlanet_s3dis_small.npz")
+    sd, extra = H.state_dict("randlanet_s3dis.manifest.json", g["weight_seed"])
+    cfg = extra["cfg"]
+    B, N = int(g["B"]), int(g["N"])
+    per = [MT.randlanet_build_inputs(synth.semantickitti_cloud(N, int(g["seed0"]) + b), num_layers=5,
+                                     ratios=cfg["sub_sampling_ratio"]) for b in range(B)]
+    inp = {k: [torch.from_numpy(np.stack([q[k][i] for q in per])) for i in range(5)]
+           for k in ("coords", "neighbor_indices", "sub_idx", "interp_idx")}
+    inp["features"] = torch.cat([inp["coords"][0], torch.from_numpy(g["extra_feat"])], -1)
+    net = M.RandLANetB200(sd, num_layers=5, sub_sampling_ratio=cfg["sub_sampling_ratio"])
+    out = net(inp)
+    assert out.shape == g["logits"].shape and rel_err(out, g["logits"]) < TOL
+    assert bool((out.argmax(-1).cpu() == torch.from_numpy(g["logits"]).argmax(-1)).float().mean() > 0.999)
+    # the device-side pyramid honours the per-level ratios
+    got = net.forward_points(inp["coords"][0], torch.from_numpy(g["extra_feat"]))
+    assert rel_err(got, g["logits"]) < TOL
