@@ -117,6 +117,11 @@ O3DML_API int o3dml_voxel_reduce(const float* points, int point_stride, const fl
                                  int feature_mode, float* out_points, float* out_features,
                                  int32_t* out_labels, void* stream);
 
+/* open3d.ml.torch.ops.reduce_subarrays_sum(values, row_splits) (ml3d/torch/models/sparseconvnet.py:318-324):
+ * out[i] = sum(values[row_splits[i] : row_splits[i+1]]), float32, sequential adds in index order. */
+O3DML_API int o3dml_reduce_subarrays_sum(const float* values, const int64_t* row_splits, int64_t num_rows,
+                                         float* out, void* stream);
+
 /* ------------------------------------------------------- PointPillars ---- */
 
 /* PillarFeatureNet.forward + PFNLayer.forward + PointPillarsScatter.forward fused

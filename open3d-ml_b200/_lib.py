@@ -41,6 +41,7 @@ _SIGNATURES = {
     "o3dml_radius_count": (I, [P, L, P, P, L, P, L, F, P, P, P, Z, P]),
     "o3dml_radius_fill": (I, [P, L, L, P, L, F, P, P, P, P, Z, P]),
     "o3dml_voxel_reduce": (I, [P, I, P, I, I, P, P, P, P, L, I, I, P, P, P, P]),
+    "o3dml_reduce_subarrays_sum": (I, [P, P, L, P, P]),
     "o3dml_nms_workspace_bytes": (Z, [L]),
     "o3dml_nms": (I, [P, P, L, F, P, P, P, Z, P]),
     "o3dml_iou_matrix": (I, [P, L, P, L, I, P, P]),

@@ -99,3 +99,29 @@ extern "C" int o3dml_voxel_reduce(const float* points, int point_stride, const f
     }
     return O3DML_OK;
 }
+
+// ---- open3d.ml.torch.ops.reduce_subarrays_sum(values, row_splits) ---------------------------------
+//   call site: ml3d/torch/models/sparseconvnet.py:318-324 (per-voxel feature sums of InputLayer).
+// out[i] = sum of values[row_splits[i] : row_splits[i+1]], sequential fp32 adds in index order (one thread per
+// segment: deterministic and bit-equal to the oracle; segments are voxels, i.e. short).
+namespace o3dml {
+__global__ void reduce_subarrays_kernel(const float* __restrict__ values, const int64_t* __restrict__ splits, int64_t rows,
+                                        float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    float acc = 0.f;
+    for (int64_t j = splits[i]; j < splits[i + 1]; ++j) acc = __fadd_rn(acc, values[j]);
+    out[i] = acc;
+}
+}  // namespace o3dml
+
+extern "C" int o3dml_reduce_subarrays_sum(const float* values, const int64_t* row_splits, int64_t num_rows, float* out,
+                                          void* stream) {
+    if (num_rows <= 0) return O3DML_OK;
+    O3DML_CHECK(values && row_splits && out, "reduce_subarrays_sum: null input");
+    o3dml::reduce_subarrays_kernel<<<(unsigned)o3dml::ceil_div<int64_t>(num_rows, 256), 256, 0, (cudaStream_t)stream>>>(
+        values, row_splits, num_rows, out);
+    O3DML_LAUNCH_CHECK();
+    o3dml_count_launches(1);
+    return O3DML_OK;
+}

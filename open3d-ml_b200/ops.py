@@ -367,3 +367,64 @@ def iou_bev(boxes_a, boxes_b):
 def iou_3d(boxes_a, boxes_b):
     """open3d.ml.contrib.iou_3d_{cpu,cuda} (ml3d/metrics/mAP.py:88): [N,7] x [M,7] (x, y, z, w, h, l, ry)."""
     return _iou(boxes_a, boxes_b, 1, 7)
+
+
+# ------------------------------------------------------------------ SparseConvUnet / op-surface ops (f3, f4)
+def reduce_subarrays_sum(values, row_splits):
+    """open3d.ml.torch.ops.reduce_subarrays_sum (ml3d/torch/models/sparseconvnet.py:318-324)."""
+    if values.dim() != 1:
+        raise RuntimeError("reduce_subarrays_sum: values must be 1-D")
+    if row_splits.dtype != torch.int64:
+        raise RuntimeError("row_splits must be int64")
+    was_cuda = values.is_cuda
+    v = _dev(values).to(torch.float32).contiguous()
+    rs = _dev(row_splits).contiguous()
+    rows = rs.numel() - 1
+    out = torch.empty((max(rows, 0),), dtype=torch.float32, device=v.device)
+    L.check(L.lib().o3dml_reduce_subarrays_sum(L.ptr(v), L.ptr(rs), rows, L.ptr(out), L.stream()))
+    out = out.to(values.dtype)
+    return out if was_cuda else out.cpu()
+
+
+VoxelPoolingResult = collections.namedtuple("VoxelPoolingResult", "pooled_positions pooled_features")
+_POOL_MODES = {"average": 0, "max": 1, "nearest_neighbor": 2, "center": 3}
+
+
+def voxel_pooling(positions, features, voxel_size, position_fn="average", feature_fn="average", debug=False):
+    """open3d.ml.torch.ops.voxel_pooling (north-star op surface; no call site in the reference): one output
+    point per occupied voxel of the grid anchored at the origin (voxel index = floor(p / voxel_size)).
+    position_fn in {average, nearest_neighbor, center}, feature_fn in {average, max, nearest_neighbor};
+    voxels come out in ascending (x + ex * (y + ey * z)) order.  'nearest_neighbor' takes the point closest to the
+    voxel centre (ties: lowest index)."""
+    if position_fn not in ("average", "nearest_neighbor", "center") or feature_fn not in ("average", "max", "nearest_neighbor"):
+        raise RuntimeError("voxel_pooling: unknown position_fn / feature_fn")
+    _check_points(positions, "positions")
+    was_cuda = positions.is_cuda
+    pts = _dev(positions).contiguous()
+    feats = _dev(features).to(torch.float32).contiguous()
+    if feats.dim() != 2 or feats.shape[0] != pts.shape[0]:
+        raise RuntimeError("voxel_pooling: features must have shape [N, C]")
+    if pts.shape[0] == 0:
+        out = VoxelPoolingResult(pts.new_zeros((0, 3)), feats.new_zeros((0, feats.shape[1])))
+        return out if was_cuda else VoxelPoolingResult(*(t.cpu() for t in out))
+    vs = float(voxel_size)
+    mm = torch.stack([pts.amin(0), pts.amax(0)]).cpu().numpy().astype(np.float32)
+    origin = (np.floor((mm[0] / np.float32(vs)).astype(np.float32)) * np.float32(vs)).astype(np.float32)
+    coords, pidx, vrs, bsp, _, counts = voxelize_raw(pts, None, [vs, vs, vs], origin, mm[1], INT64_MAX, INT64_MAX)
+    m = int(counts[0].item())
+    if "nearest_neighbor" in (position_fn, feature_fn):
+        # reorder every voxel's point list so that its first entry is the point nearest to the voxel centre
+        centre = (coords[:m].to(torch.float32) + 0.5) * vs + torch.from_numpy(origin).to(pts.device)
+        vid = torch.repeat_interleave(torch.arange(m, device=pts.device), (vrs[1:m + 1] - vrs[:m]))
+        d2 = ((pts[pidx[:vid.numel()]] - centre[vid]) ** 2).sum(1)
+        order = torch.argsort(d2, stable=True)
+        order = order[torch.argsort(vid[order], stable=True)]
+        pidx = pidx.clone()
+        pidx[:vid.numel()] = pidx[:vid.numel()][order]
+    pm = {"average": 0, "nearest_neighbor": 2, "center": 2}[position_fn]
+    fm = {"average": 0, "max": 1, "nearest_neighbor": 2}[feature_fn]
+    op, of, _ = voxel_reduce(pts, feats, None, vrs, pidx, counts, m, position_mode=pm, feature_mode=fm)
+    if position_fn == "center":
+        op = (coords[:m].to(torch.float32) + 0.5) * vs + torch.from_numpy(origin).to(pts.device)
+    out = VoxelPoolingResult(op, of)
+    return out if was_cuda else VoxelPoolingResult(*(t.cpu() for t in out))

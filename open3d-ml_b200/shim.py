@@ -76,6 +76,32 @@ class _AddictDict(dict):
         return type(self)(self)
 
 
+class _AliasFinder:
+    """`from open3d.ml.utils import Config` / `import open3d.ml.torch.models` go through the import system,
+    not through attribute access: resolve `open3d.ml.<x>` -> `ml3d.<x>` and `open3d.ml.torch.<x>` -> `ml3d.torch.<x>`
+    and register the SAME module object under both names (the mechanism of README.md:313-314)."""
+
+    FABRICATED = ("open3d.ml.torch.ops", "open3d.ml.torch.layers", "open3d.ml.contrib")
+
+    def find_spec(self, name, path=None, target=None):
+        if not name.startswith("open3d.ml.") or name.startswith(self.FABRICATED):
+            return None
+        real = "ml3d." + name[len("open3d.ml."):]
+        try:
+            mod = importlib.import_module(real)
+        except ImportError:
+            return None
+        from importlib.machinery import ModuleSpec
+
+        class _Loader:
+            def create_module(self, spec):
+                return mod
+
+            def exec_module(self, module):
+                pass
+        return ModuleSpec(name, _Loader(), is_package=hasattr(mod, "__path__"))
+
+
 _INSTALLED = False
 
 
@@ -144,6 +170,7 @@ def install(ml3d_root=None):
                     raise AttributeError(attr)
                 return importlib.import_module(prefix + "." + attr)
             return getter
+        sys.meta_path.insert(0, _AliasFinder())
         ml.__getattr__ = lazy("ml3d")              # open3d.ml.utils / datasets / vis / configs
         mlt_get = lazy("ml3d.torch")               # open3d.ml.torch.models / pipelines / ...
 

@@ -78,6 +78,9 @@ def test_shim_exposes_the_reference_tree_unmodified():
             "import open3d as o3d, open3d.ml as _ml3d, open3d.ml.torch as ml3d\n"
             "from open3d.ml.torch.ops import voxelize, ragged_to_dense\n"
             "from open3d.ml.torch.layers import FixedRadiusSearch\n"
+            "from open3d.ml.utils import Config as _C2\n"
+            "from open3d.ml.torch.models import RandLANet as _R2\n"
+            "import ml3d.utils as _mu; assert _C2 is _mu.Config\n"
             "import open3d.core as o3c\n"
             "assert o3d._build_config['BUILD_PYTORCH_OPS'] and o3c.nns.NearestNeighborSearch\n"
             "cfg = _ml3d.utils.Config.load_from_file('/root/reference/ml3d/configs/randlanet_semantickitti.yml')\n"
