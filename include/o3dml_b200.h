@@ -140,6 +140,34 @@ O3DML_API int o3dml_pp_pfn_scatter(const float* points, int point_stride, int po
                          int max_points_per_voxel, float* feat_out, float* canvas,
                          int canvas_nchw, void* stream);
 
+/* Neighbour table of open3d.ml.torch.layers.SparseConv / SparseConvTranspose
+ *   (ml3d/torch/models/sparseconvnet.py:344-485): neighbors int32 [num_out, kx*ky*kz] = id of the input point
+ *   in kernel cell (x, y, z) (row-major, the layout of the layer's `kernel` parameter [kx, ky, kz, Cin, Cout])
+ *   of each output, or num_in when the cell is empty; neighbor_count int32 [num_out] (may be NULL) = non-empty
+ *   cells (the `normalize` divisor).  cell_a = floor((in_a - out_a) / voxel_size + offset_a + ks_a / 2), with
+ *   in / out swapped for the transposed convolution.  The contraction is o3dml_linear(_tc) with the table
+ *   columns as index operands. */
+O3DML_API size_t o3dml_sparse_conv_workspace_bytes(int64_t num_in);
+O3DML_API int o3dml_sparse_conv_neighbors(const float* in_positions, int64_t num_in,
+                                          const float* out_positions, int64_t num_out, float voxel_size,
+                                          const float* h_offset, const int* h_kernel_size, int transpose,
+                                          int32_t* neighbors, int32_t* neighbor_count, void* workspace,
+                                          size_t workspace_bytes, void* stream);
+
+/* open3d.ml.torch.ops.continuous_conv (op surface named by the north star; no call site in the reference):
+ *   out[o] = sum_n imp_n * W(map((inp_pos[n] - out_pos[o]) * 2 / extent + offset))^T f[n] over the neighbour list
+ *   [neighbors_row_splits[o], neighbors_row_splits[o+1]) of neighbors_index; filters [size_z, size_y, size_x, Cin, Cout];
+ *   coordinate_mapping 0 identity / 1 ball_to_cube_radial; interpolation 0 nearest / 1 linear (clamped) /
+ *   2 linear_border (zero outside); normalize divides by the sum of the importances (or the neighbour count). */
+O3DML_API int o3dml_continuous_conv(const float* filters, int size_x, int size_y, int size_z, int in_channels,
+                                    int out_channels, const float* out_positions, int64_t num_out,
+                                    const float* extents, int extents_per_point, const float* h_offset,
+                                    const float* inp_positions, const float* inp_features, int64_t num_inp,
+                                    const float* inp_importance, const void* neighbors_index, int index_is64,
+                                    const float* neighbors_importance, const int64_t* neighbors_row_splits,
+                                    int align_corners, int coordinate_mapping, int normalize, int interpolation,
+                                    float* out, void* stream);
+
 /* ------------------------------------------- detection post-processing ---- */
 
 /* open3d.ml.torch.ops.nms(boxes, scores, nms_overlap_thresh) -- rotated-BEV greedy NMS

@@ -42,6 +42,9 @@ _SIGNATURES = {
     "o3dml_radius_fill": (I, [P, L, L, P, L, F, P, P, P, P, Z, P]),
     "o3dml_voxel_reduce": (I, [P, I, P, I, I, P, P, P, P, L, I, I, P, P, P, P]),
     "o3dml_reduce_subarrays_sum": (I, [P, P, L, P, P]),
+    "o3dml_sparse_conv_workspace_bytes": (Z, [L]),
+    "o3dml_sparse_conv_neighbors": (I, [P, L, P, L, F, P, P, I, P, P, P, Z, P]),
+    "o3dml_continuous_conv": (I, [P, I, I, I, I, I, P, L, P, I, P, P, P, L, P, P, I, P, P, I, I, I, I, P, P]),
     "o3dml_nms_workspace_bytes": (Z, [L]),
     "o3dml_nms": (I, [P, P, L, F, P, P, P, Z, P]),
     "o3dml_iou_matrix": (I, [P, L, P, L, I, P, P]),
@@ -190,7 +193,7 @@ def pack_linear(w_kc):
     return PackedWeight(w_kc)
 
 
-TC_MIN_K = int(os.environ.get("O3DML_GEMM_TC_MIN_K", "128"))
+TC_MIN_K = int(os.environ.get("O3DML_GEMM_TC_MIN_K", "64"))
 
 
 def _tc_ok(srcs):

@@ -428,3 +428,80 @@ def voxel_pooling(positions, features, voxel_size, position_fn="average", featur
         op = (coords[:m].to(torch.float32) + 0.5) * vs + torch.from_numpy(origin).to(pts.device)
     out = VoxelPoolingResult(op, of)
     return out if was_cuda else VoxelPoolingResult(*(t.cpu() for t in out))
+
+
+_CCONV_MAPPING = {"identity": 0, "ball_to_cube_radial": 1}
+_CCONV_INTERP = {"nearest_neighbor": 0, "linear": 1, "linear_border": 2}
+
+
+def continuous_conv(filters, out_positions, extents, offset, inp_positions, inp_features, inp_importance,
+                    neighbors_index, neighbors_importance, neighbors_row_splits, align_corners=False,
+                    coordinate_mapping="ball_to_cube_radial", normalize=False, interpolation="linear",
+                    max_temp_mem_MB=64):
+    """open3d.ml.torch.ops.continuous_conv (raw op; contract in csrc/cconv.cu).  filters [Sz, Sy, Sx, Cin, Cout];
+    empty importance tensors mean "all ones"; extents [1] or [num_out]."""
+    if coordinate_mapping not in _CCONV_MAPPING:
+        raise RuntimeError("continuous_conv: coordinate_mapping '%s' is not implemented (identity, ball_to_cube_radial)"
+                           % coordinate_mapping)
+    if interpolation not in _CCONV_INTERP:
+        raise RuntimeError("continuous_conv: unknown interpolation '%s'" % interpolation)
+    if filters.dim() != 5:
+        raise RuntimeError("continuous_conv: filters must have shape [Sz, Sy, Sx, Cin, Cout]")
+    was_cuda = inp_features.is_cuda
+    f = _dev(filters).to(torch.float32).contiguous()
+    op, ip = _dev(out_positions).to(torch.float32).contiguous(), _dev(inp_positions).to(torch.float32).contiguous()
+    feat = _dev(inp_features).to(torch.float32).contiguous()
+    ext = _dev(torch.as_tensor(extents, dtype=torch.float32).reshape(-1)).contiguous()
+    if ext.numel() not in (1, op.shape[0]):
+        raise RuntimeError("continuous_conv: extents must have 1 or num_out elements")
+    off = np.ascontiguousarray(torch.as_tensor(offset).detach().cpu().numpy(), dtype=np.float32).reshape(3)
+    imp = None if inp_importance is None or inp_importance.numel() == 0 else _dev(inp_importance).float().contiguous()
+    nimp = (None if neighbors_importance is None or neighbors_importance.numel() == 0
+            else _dev(neighbors_importance).float().contiguous())
+    idx = _dev(neighbors_index).contiguous()
+    if idx.dtype not in (torch.int32, torch.int64):
+        raise RuntimeError("continuous_conv: neighbors_index must be int32 or int64")
+    rs = _dev(neighbors_row_splits).to(torch.int64).contiguous()
+    if rs.numel() != op.shape[0] + 1:
+        raise RuntimeError("continuous_conv: neighbors_row_splits must have num_out + 1 elements")
+    sz, sy, sx, cin, cout = f.shape
+    if feat.shape[1] != cin:
+        raise RuntimeError("continuous_conv: feature channels do not match the filter")
+    out = torch.empty((op.shape[0], cout), dtype=torch.float32, device=f.device)
+    L.check(L.lib().o3dml_continuous_conv(
+        L.ptr(f), sx, sy, sz, cin, cout, L.ptr(op), op.shape[0], L.ptr(ext), 1 if ext.numel() > 1 else 0,
+        off.ctypes.data, L.ptr(ip), L.ptr(feat), ip.shape[0], L.ptr(imp), L.ptr(idx),
+        1 if idx.dtype == torch.int64 else 0, L.ptr(nimp), L.ptr(rs), 1 if align_corners else 0,
+        _CCONV_MAPPING[coordinate_mapping], 1 if normalize else 0, _CCONV_INTERP[interpolation], L.ptr(out), L.stream()))
+    return out if was_cuda else out.cpu()
+
+
+def sparse_conv(filters, inp_features, inp_importance, neighbors_index, neighbors_kernel_index, neighbors_importance,
+                neighbors_row_splits, normalize=False, max_temp_mem_MB=64):
+    """open3d.ml.torch.ops.sparse_conv (raw op): out[o] = sum_j filters[kernel_index[j]]^T f[neighbors_index[j]] over
+    the ragged rows of `neighbors_row_splits`; filters [.., Cin, Cout] with the leading dims flattened into the kernel
+    index.  Runs as gathered tensor-core GEMMs over a dense [num_out, kernel_cells] table (one neighbour per cell)."""
+    if (inp_importance is not None and inp_importance.numel()) or \
+            (neighbors_importance is not None and neighbors_importance.numel()):
+        raise RuntimeError("sparse_conv: importance is not implemented")
+    was_cuda = inp_features.is_cuda
+    w = filters.detach().float().cpu()
+    cin, cout = w.shape[-2], w.shape[-1]
+    w = w.reshape(-1, cin, cout)
+    kc = w.shape[0]
+    feat = _dev(inp_features).to(torch.float32).contiguous()
+    rs = _dev(neighbors_row_splits).to(torch.int64)
+    m = rs.numel() - 1
+    lens = rs[1:] - rs[:-1]
+    rows = torch.repeat_interleave(torch.arange(m, device=feat.device), lens)
+    table = torch.full((m, kc), feat.shape[0], dtype=torch.int32, device=feat.device)
+    table[rows, _dev(neighbors_kernel_index).long()] = _dev(neighbors_index).to(torch.int32)
+    out = torch.zeros((m, cout), dtype=torch.float32, device=feat.device)
+    for gi, c0 in enumerate(range(0, kc, 3)):
+        c1 = min(c0 + 3, kc)
+        pw = L.pack_linear(w[c0:c1].reshape((c1 - c0) * cin, cout))
+        srcs = [L.make_src(feat, index=table[:, c:], index_ld=kc) for c in range(c0, c1)]
+        L.linear(srcs, pw, out, None, None, residual=out if gi else None, act=None)
+    if normalize:
+        out = out / lens.clamp_min(1).to(torch.float32).unsqueeze(1)
+    return out if was_cuda else out.cpu()

@@ -130,14 +130,13 @@ def install(ml3d_root=None):
     _module("open3d.ml.torch.ops", voxelize=O.voxelize, ragged_to_dense=O.ragged_to_dense,
             knn_search=O.knn_search, fixed_radius_search=O.fixed_radius_search,
             nms=O.nms,
-            reduce_subarrays_sum=_not_on_hot_path("ops.reduce_subarrays_sum"),
-            voxel_pooling=_not_on_hot_path("ops.voxel_pooling"),
-            continuous_conv=_not_on_hot_path("ops.continuous_conv"),
-            sparse_conv=_not_on_hot_path("ops.sparse_conv"))
-    stub_layer = type("SparseConvNotOnHotPath", (torch.nn.Module,),
-                      {"__init__": lambda self, *a, **k: _not_on_hot_path("layers.SparseConv")()})
+            reduce_subarrays_sum=O.reduce_subarrays_sum,
+            voxel_pooling=O.voxel_pooling,
+            continuous_conv=O.continuous_conv, sparse_conv=O.sparse_conv)
+    from . import layers as LY
     _module("open3d.ml.torch.layers", FixedRadiusSearch=O.FixedRadiusSearch, KNNSearch=O.KNNSearch,
-            SparseConv=stub_layer, SparseConvTranspose=stub_layer)
+            SparseConv=LY.SparseConv, SparseConvTranspose=LY.SparseConvTranspose,
+            ContinuousConv=LY.ContinuousConv)
     _module("open3d.ml.contrib", subsample=O.subsample, subsample_batch=O.subsample_batch,
             iou_bev_cpu=O.iou_bev, iou_bev_cuda=O.iou_bev, iou_3d_cpu=O.iou_3d, iou_3d_cuda=O.iou_3d)
     vis = _module("open3d.visualization")

@@ -345,3 +345,53 @@ def np_rbox_area_mc(a, b, samples=400000, seed=0):
         u, v = d[:, 0] * c + d[:, 1] * s, -d[:, 0] * s + d[:, 1] * c
         return (np.abs(u) <= bx[2] / 2) & (np.abs(v) <= bx[3] / 2)
     return float(np.mean(inside(a) & inside(b)) * np.prod(hi - lo))
+
+
+# ----------------------------------------------------------------------------
+# sparse convolution / segment sums (contract: ops_ref.c)
+# ----------------------------------------------------------------------------
+def c_sparse_conv(feat, in_pos, out_pos, voxel_size, offset, kernel, bias=None, normalize=False, transpose=False):
+    feat, in_pos, out_pos, kernel = _f32(feat), _f32(in_pos), _f32(out_pos), _f32(kernel)
+    ks = np.ascontiguousarray(kernel.shape[:3], np.int32)
+    cin, cout = kernel.shape[3], kernel.shape[4]
+    off = _f32(offset).reshape(3)
+    out = np.zeros((len(out_pos), cout), np.float32)
+    b = None if bias is None else _f32(bias)
+    rc = lib().oracle_sparse_conv(_p(feat, ctypes.c_float), _p(in_pos, ctypes.c_float), ctypes.c_int64(len(in_pos)),
+                                  _p(out_pos, ctypes.c_float), ctypes.c_int64(len(out_pos)), ctypes.c_float(voxel_size),
+                                  _p(off, ctypes.c_float), _p(ks, ctypes.c_int), ctypes.c_int(int(transpose)),
+                                  _p(kernel, ctypes.c_float), ctypes.c_int(cin), ctypes.c_int(cout),
+                                  _p(b, ctypes.c_float) if b is not None else None, ctypes.c_int(int(normalize)),
+                                  _p(out, ctypes.c_float))
+    assert rc == 0
+    return out
+
+
+def c_reduce_subarrays_sum(values, row_splits):
+    values, rs = _f32(values), np.ascontiguousarray(row_splits, np.int64)
+    out = np.zeros(len(rs) - 1, np.float32)
+    assert lib().oracle_reduce_subarrays_sum(_p(values, ctypes.c_float), _p(rs, ctypes.c_int64),
+                                             ctypes.c_int64(len(rs) - 1), _p(out, ctypes.c_float)) == 0
+    return out
+
+
+def c_continuous_conv(filters, out_pos, extents, offset, inp_pos, feat, inp_imp, nbr, nbr_imp, splits,
+                      align_corners, mapping, normalize, interp):
+    """mapping / interp are the integer codes of cconv.cu."""
+    filters, out_pos, inp_pos, feat = _f32(filters), _f32(out_pos), _f32(inp_pos), _f32(feat)
+    ext = _f32(np.asarray(extents).reshape(-1))
+    sz, sy, sx, cin, cout = filters.shape
+    nbr = np.ascontiguousarray(nbr, np.int64)
+    splits = np.ascontiguousarray(splits, np.int64)
+    out = np.zeros((len(out_pos), cout), np.float32)
+    ii = None if inp_imp is None else _f32(inp_imp)
+    ni = None if nbr_imp is None else _f32(nbr_imp)
+    off = _f32(offset).reshape(3)
+    rc = lib().oracle_continuous_conv(
+        _p(filters, ctypes.c_float), sx, sy, sz, cin, cout, _p(out_pos, ctypes.c_float), ctypes.c_int64(len(out_pos)),
+        _p(ext, ctypes.c_float), int(len(ext) > 1), _p(off, ctypes.c_float), _p(inp_pos, ctypes.c_float),
+        _p(feat, ctypes.c_float), _p(ii, ctypes.c_float) if ii is not None else None, _p(nbr, ctypes.c_int64),
+        _p(ni, ctypes.c_float) if ni is not None else None, _p(splits, ctypes.c_int64), int(align_corners), int(mapping),
+        int(normalize), int(interp), _p(out, ctypes.c_float))
+    assert rc == 0
+    return out

@@ -390,3 +390,122 @@ EXPORT int64_t oracle_nms(const float *boxes, const float *scores, int64_t n, fl
     free(order);
     return kept;
 }
+
+/* ------------------------------------------------------------ sparse conv ---- */
+/* open3d.ml.torch.layers.SparseConv / SparseConvTranspose as consumed at
+ * ml3d/torch/models/sparseconvnet.py:344-485 (PARITY UNPINNED).  Brute force over all (output, input) pairs:
+ *   cell_a = floor((in_a - out_a) / v + offset_a + ks_a / 2)   (in / out swapped when transpose)
+ *   out[o] += kernel[cell]^T f[in]   for every input whose three cells are in range (ALL of them: on the
+ *   voxel-unique inputs the model produces this equals the product's one-input-per-cell table);
+ *   normalize: divide by the number of contributing inputs; bias added last.  float64 accumulation. */
+EXPORT int oracle_sparse_conv(const float *feat, const float *in_pos, int64_t n, const float *out_pos, int64_t m,
+                              float v, const float *offset, const int *ks, int transpose, const float *kernel,
+                              int cin, int cout, const float *bias, int normalize, float *out) {
+    float inv_v = 1.0f / v;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t o = 0; o < m; ++o) {
+        double *acc = (double *)calloc((size_t)cout, sizeof(double));
+        int64_t cnt = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            int cell[3], ok = 1;
+            for (int a = 0; a < 3 && ok; ++a) {
+                float d = transpose ? (out_pos[3 * o + a] - in_pos[3 * i + a]) : (in_pos[3 * i + a] - out_pos[3 * o + a]);
+                volatile float r0 = d * inv_v;
+                volatile float r1 = r0 + offset[a];
+                volatile float r = r1 + 0.5f * (float)ks[a];
+                int c = (int)floorf(r);
+                if (c < 0 || c >= ks[a]) ok = 0;
+                cell[a] = c;
+            }
+            if (!ok) continue;
+            ++cnt;
+            const float *w = kernel + (size_t)((cell[0] * ks[1] + cell[1]) * ks[2] + cell[2]) * cin * cout;
+            for (int ci = 0; ci < cin; ++ci) {
+                double f = feat[i * cin + ci];
+                for (int co = 0; co < cout; ++co) acc[co] += f * (double)w[ci * cout + co];
+            }
+        }
+        for (int co = 0; co < cout; ++co) {
+            double x = acc[co];
+            if (normalize && cnt > 0) x /= (double)cnt;
+            if (bias) x += bias[co];
+            out[o * cout + co] = (float)x;
+        }
+        free(acc);
+    }
+    return 0;
+}
+
+/* out[i] = sum(values[splits[i] : splits[i+1]]), sequential float32 adds (reduce_subarrays_sum, sparseconvnet.py:318) */
+EXPORT int oracle_reduce_subarrays_sum(const float *values, const int64_t *splits, int64_t rows, float *out) {
+    for (int64_t i = 0; i < rows; ++i) {
+        volatile float acc = 0.f;
+        for (int64_t j = splits[i]; j < splits[i + 1]; ++j) acc = acc + values[j];
+        out[i] = acc;
+    }
+    return 0;
+}
+
+/* --------------------------------------------------------- continuous conv ---- */
+/* open3d.ml.torch.ops.continuous_conv (no call site in the reference; PARITY UNPINNED).  Contract: cconv.cu header.
+ * mapping 0 identity / 1 ball_to_cube_radial; interp 0 nearest / 1 linear (clamped) / 2 linear_border. */
+EXPORT int oracle_continuous_conv(const float *filters, int sx, int sy, int sz, int cin, int cout,
+                                  const float *out_pos, int64_t m, const float *extents, int per_point,
+                                  const float *offset, const float *inp_pos, const float *feat,
+                                  const float *inp_imp, const int64_t *nbr, const float *nbr_imp,
+                                  const int64_t *splits, int align_corners, int mapping, int normalize, int interp,
+                                  float *out) {
+    const int S[3] = {sx, sy, sz};
+    for (int64_t o = 0; o < m; ++o) {
+        double *acc = (double *)calloc((size_t)cout, sizeof(double));
+        double norm = 0;
+        double ext = extents[per_point ? o : 0];
+        for (int64_t j = splits[o]; j < splits[o + 1]; ++j) {
+            int64_t n = nbr[j];
+            double imp = (nbr_imp ? nbr_imp[j] : 1.0) * (inp_imp ? inp_imp[n] : 1.0);
+            norm += imp;
+            double q[3];
+            for (int a = 0; a < 3; ++a)
+                q[a] = ((double)inp_pos[3 * n + a] - out_pos[3 * o + a]) * (ext > 0 ? 2.0 / ext : 0.0) + offset[a];
+            if (mapping == 1) {
+                double n2 = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+                double ni = fmax(fabs(q[0]), fmax(fabs(q[1]), fabs(q[2])));
+                double s = ni > 0 ? n2 / ni : 0;
+                for (int a = 0; a < 3; ++a) q[a] *= s;
+            }
+            double u[3];
+            for (int a = 0; a < 3; ++a)
+                u[a] = align_corners ? (q[a] + 1) * 0.5 * (S[a] - 1) : (q[a] + 1) * 0.5 * S[a] - 0.5;
+            int ncorner = interp == 0 ? 1 : 8;
+            for (int c = 0; c < ncorner; ++c) {
+                int ii[3];
+                double w = 1;
+                int inside = 1;
+                for (int a = 0; a < 3; ++a) {
+                    int i;
+                    if (interp == 0) {
+                        i = (int)floor(u[a] + 0.5);
+                    } else {
+                        int bit = (c >> a) & 1;
+                        double fl = floor(u[a]);
+                        i = (int)fl + bit;
+                        w *= bit ? (u[a] - fl) : 1 - (u[a] - fl);
+                    }
+                    if (i < 0 || i >= S[a]) { inside = 0; i = i < 0 ? 0 : S[a] - 1; }
+                    ii[a] = i;
+                }
+                if (interp == 2 && !inside) w = 0;
+                if (w == 0) continue;
+                const float *wt = filters + (size_t)((ii[2] * S[1] + ii[1]) * S[0] + ii[0]) * cin * cout;
+                for (int ci = 0; ci < cin; ++ci) {
+                    double fv = feat[n * cin + ci] * imp * w;
+                    for (int co = 0; co < cout; ++co) acc[co] += fv * wt[ci * cout + co];
+                }
+            }
+        }
+        for (int co = 0; co < cout; ++co)
+            out[o * cout + co] = (float)((normalize && norm != 0) ? acc[co] / norm : acc[co]);
+        free(acc);
+    }
+    return 0;
+}

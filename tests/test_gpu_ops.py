@@ -287,3 +287,148 @@ def test_nms_empty_and_bad_shapes():
     assert M.nms(torch.zeros(0, 5).cuda(), torch.zeros(0).cuda(), 0.5).numel() == 0
     with pytest.raises(RuntimeError):
         M.nms(torch.zeros(4, 4).cuda(), torch.zeros(4).cuda(), 0.5)
+
+
+# ------------------------------------------------------------------ SparseConvUnet ops (f3) + voxel_pooling (f4)
+def _sparse_lattice(n_vox, grid, seed):
+    rng = np.random.default_rng(seed)
+    ii = np.unique(rng.integers(0, grid, (n_vox, 3)), axis=0)
+    return ii.astype(np.int64)
+
+
+@pytest.mark.parametrize("cin,cout,normalize,bias", [(32, 64, False, False), (64, 32, True, True), (5, 7, False, True)])
+def test_sparse_conv_layers_vs_oracle(cin, cout, normalize, bias):
+    """SubmanifoldSparseConv (3^3, offset 0), Convolution (2^3, offset -0.5, onto calculate_grid's coarse lattice)
+    and DeConvolution (transposed 2^3) of sparseconvnet.py:344-485 against the brute-force oracle, whose cell
+    formula is itself pinned to torch conv3d / conv_transpose3d (tests/test_oracle_ops.py)."""
+    from open3d_ml_b200 import layers as LY
+    from oracle import ops as O
+    ii = _sparse_lattice(3000, 24, 11)
+    pos = (ii + 0.5).astype(np.float32)
+    rng = np.random.default_rng(12)
+    feat = rng.standard_normal((len(pos), cin)).astype(np.float32)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        # submanifold
+        conv = LY.SparseConv(cin, cout, [3, 3, 3], use_bias=bias, normalize=normalize, offset=torch.zeros(3)).eval()
+        if bias:
+            conv.bias.normal_()
+        got = conv(torch.from_numpy(feat), torch.from_numpy(pos), torch.from_numpy(pos), 1.0)
+        ref = O.c_sparse_conv(feat, pos, pos, 1.0, [0, 0, 0], conv.kernel.numpy(), conv.bias.numpy() if bias else None,
+                              normalize)
+        assert not got.is_cuda and rel_err(got, ref) < 1e-4
+        # strided down
+        coarse = (np.unique(ii - ii % 2, axis=0) + 0.5).astype(np.float32)
+        down = LY.SparseConv(cin, cout, [2, 2, 2], use_bias=bias, normalize=normalize, offset=torch.full((3,), -0.5)).eval()
+        got = down(torch.from_numpy(feat).cuda(), torch.from_numpy(pos).cuda(), torch.from_numpy(coarse).cuda(), 1.0)
+        ref = O.c_sparse_conv(feat, pos, coarse, 1.0, [-0.5] * 3, down.kernel.numpy(), down.bias.numpy() if bias else None,
+                              normalize)
+        assert got.is_cuda and rel_err(got, ref) < 1e-4
+        # transposed up
+        cf = rng.standard_normal((len(coarse), cin)).astype(np.float32)
+        up = LY.SparseConvTranspose(cin, cout, [2, 2, 2], use_bias=bias, normalize=normalize, offset=torch.full((3,), -0.5)).eval()
+        got = up(torch.from_numpy(cf), torch.from_numpy(coarse), torch.from_numpy(pos), 1.0)
+        ref = O.c_sparse_conv(cf, coarse, pos, 1.0, [-0.5] * 3, up.kernel.numpy(), up.bias.numpy() if bias else None,
+                              normalize, transpose=True)
+        assert rel_err(got, ref) < 1e-4
+        # state_dict keys are the upstream layer's
+        assert set(k for k in conv.state_dict() if k != "offset") == ({"kernel", "bias"} if bias else {"kernel"})
+
+
+def test_reduce_subarrays_sum_and_voxel_pooling():
+    import open3d_ml_b200 as M
+    from oracle import ops as O
+    rng = np.random.default_rng(13)
+    vals = rng.standard_normal(5000).astype(np.float32)
+    rs = np.concatenate([[0], np.sort(rng.integers(0, 5000, 300)), [5000]]).astype(np.int64)
+    got = M.ops.reduce_subarrays_sum(torch.from_numpy(vals).cuda(), torch.from_numpy(rs).cuda())
+    assert np.array_equal(got.cpu().numpy(), O.c_reduce_subarrays_sum(vals, rs))
+    pts = (rng.random((4000, 3)) * 3).astype(np.float32)
+    feats = rng.standard_normal((4000, 6)).astype(np.float32)
+    r = M.ops.voxel_pooling(torch.from_numpy(pts).cuda(), torch.from_numpy(feats).cuda(), 0.5, "average", "max")
+    vox = np.floor(pts / 0.5).astype(np.int64)
+    keys = vox[:, 0] + 100 * (vox[:, 1] + 100 * vox[:, 2])
+    uk = np.unique(keys)
+    assert r.pooled_positions.shape == (len(uk), 3) and r.pooled_features.shape == (len(uk), 6)
+    order = np.argsort(keys, kind="stable")
+    ks = keys[order]
+    first = np.searchsorted(ks, uk)
+    last = np.searchsorted(ks, uk, side="right")
+    ref_f = np.stack([feats[order[a:b]].max(0) for a, b in zip(first, last)])
+    ref_p = np.stack([pts[order[a:b]].astype(np.float64).mean(0) for a, b in zip(first, last)])
+    assert np.array_equal(r.pooled_features.cpu().numpy(), ref_f)
+    assert np.abs(r.pooled_positions.cpu().numpy() - ref_p).max() < 1e-5
+    c = M.ops.voxel_pooling(torch.from_numpy(pts), torch.from_numpy(feats), 0.5, "center", "nearest_neighbor")
+    assert not c.pooled_positions.is_cuda
+    assert np.allclose(c.pooled_positions.numpy(), (np.floor(ref_p / 0.5) + 0.5) * 0.5)
+    d2 = ((pts - (np.floor(pts / 0.5) + 0.5) * 0.5) ** 2).sum(1)
+    nn = np.array([order[a:b][np.argmin(d2[order[a:b]])] for a, b in zip(first, last)])
+    assert np.array_equal(c.pooled_features.numpy(), feats[nn])
+
+
+@pytest.mark.parametrize("mapping,interp,align,normalize", [("identity", "nearest_neighbor", True, False),
+                                                             ("ball_to_cube_radial", "linear", True, True),
+                                                             ("ball_to_cube_radial", "linear_border", False, False),
+                                                             ("identity", "linear", False, True)])
+def test_continuous_conv_op_and_layer_vs_oracle(mapping, interp, align, normalize):
+    import open3d_ml_b200 as M
+    from open3d_ml_b200 import layers as LY
+    from oracle import ops as O
+    rng = np.random.default_rng(21)
+    n, m, cin, cout = 600, 200, 6, 10
+    ip = rng.random((n, 3)).astype(np.float32)
+    op = rng.random((m, 3)).astype(np.float32)
+    feat = rng.standard_normal((n, cin)).astype(np.float32)
+    filt = rng.standard_normal((3, 4, 5, cin, cout)).astype(np.float32)
+    ext = 0.5
+    idx, rs, _ = O.c_radius(ip, op, ext / 2)
+    imp = rng.random(n).astype(np.float32)
+    ref = O.c_continuous_conv(filt, op, [ext], [0.1, 0, -0.1], ip, feat, imp, idx, None, rs, align,
+                              {"identity": 0, "ball_to_cube_radial": 1}[mapping], normalize,
+                              {"nearest_neighbor": 0, "linear": 1, "linear_border": 2}[interp])
+    got = M.ops.continuous_conv(torch.from_numpy(filt).cuda(), torch.from_numpy(op).cuda(), torch.tensor([ext]),
+                                torch.tensor([0.1, 0, -0.1]), torch.from_numpy(ip).cuda(), torch.from_numpy(feat).cuda(),
+                                torch.from_numpy(imp).cuda(), torch.from_numpy(idx).cuda(), torch.empty(0),
+                                torch.from_numpy(rs).cuda(), align, mapping, normalize, interp)
+    assert rel_err(got, ref) < 1e-4
+    with torch.no_grad():
+        layer = LY.ContinuousConv(cin, cout, [3, 3, 3], align_corners=align, coordinate_mapping=mapping,
+                                  interpolation=interp, normalize=normalize, use_bias=True).eval()
+        layer.bias.normal_()
+        out = layer(torch.from_numpy(feat), torch.from_numpy(ip), torch.from_numpy(op), ext)
+        ref2 = O.c_continuous_conv(layer.kernel.numpy(), op, [ext], [0, 0, 0], ip, feat, None, idx, None, rs, align,
+                                   {"identity": 0, "ball_to_cube_radial": 1}[mapping], normalize,
+                                   {"nearest_neighbor": 0, "linear": 1, "linear_border": 2}[interp]) + layer.bias.numpy()
+    assert rel_err(out, ref2) < 1e-4
+    with pytest.raises(RuntimeError):
+        M.ops.continuous_conv(torch.from_numpy(filt), torch.from_numpy(op), torch.tensor([ext]), torch.zeros(3),
+                              torch.from_numpy(ip), torch.from_numpy(feat), None, torch.from_numpy(idx), None,
+                              torch.from_numpy(rs), coordinate_mapping="ball_to_cube_volume_preserving")
+
+
+def test_raw_sparse_conv_op_vs_dense_table():
+    import open3d_ml_b200 as M
+    from oracle import ops as O
+    ii = _sparse_lattice(800, 12, 31)
+    pos = (ii + 0.5).astype(np.float32)
+    rng = np.random.default_rng(32)
+    cin, cout = 32, 16
+    feat = rng.standard_normal((len(pos), cin)).astype(np.float32)
+    k = rng.standard_normal((3, 3, 3, cin, cout)).astype(np.float32)
+    ref = O.c_sparse_conv(feat, pos, pos, 1.0, [0, 0, 0], k)
+    # ragged neighbour lists (index, kernel cell) of the 27-neighbourhood, built on the host
+    key = {tuple(v): i for i, v in enumerate(ii)}
+    nidx, kidx, rs = [], [], [0]
+    for v in ii:
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    j = key.get((v[0] + dx, v[1] + dy, v[2] + dz))
+                    if j is not None:
+                        nidx.append(j)
+                        kidx.append(((dx + 1) * 3 + (dy + 1)) * 3 + (dz + 1))
+        rs.append(len(nidx))
+    got = M.ops.sparse_conv(torch.from_numpy(k), torch.from_numpy(feat).cuda(), torch.empty(0),
+                            torch.tensor(nidx, dtype=torch.int32).cuda(), torch.tensor(kidx, dtype=torch.uint8).cuda(),
+                            torch.empty(0), torch.tensor(rs, dtype=torch.int64).cuda())
+    assert rel_err(got, ref) < 1e-4

@@ -181,3 +181,72 @@ def test_nms_oracle_is_greedy_by_score():
     keep, _ = O.c_nms(boxes, scores, 0.99)
     assert list(keep) == [1, 3, 0, 2]
     assert len(O.c_nms(boxes[:0], scores[:0], 0.5)[0]) == 0
+
+
+def test_sparse_conv_oracle_equals_dense_conv3d_on_a_full_lattice():
+    """On a fully occupied lattice the submanifold 3x3x3 SparseConv (offset 0) is an ordinary zero-padded 3-D
+    cross-correlation: checks the cell formula and the [kx, ky, kz, Cin, Cout] kernel layout against torch."""
+    import torch
+    from oracle import ops as O
+    rng = np.random.default_rng(0)
+    G, cin, cout = 5, 3, 4
+    ii = np.stack(np.meshgrid(np.arange(G), np.arange(G), np.arange(G), indexing="ij"), -1).reshape(-1, 3)
+    pos = (ii + 0.5).astype(np.float32)
+    feat = rng.standard_normal((len(pos), cin)).astype(np.float32)
+    kernel = rng.standard_normal((3, 3, 3, cin, cout)).astype(np.float32)
+    got = O.c_sparse_conv(feat, pos, pos, 1.0, [0, 0, 0], kernel)
+    vol = torch.from_numpy(feat).view(1, G, G, G, cin).permute(0, 4, 1, 2, 3)            # [1, C, x, y, z]
+    w = torch.from_numpy(kernel).permute(4, 3, 0, 1, 2)                                  # [Cout, Cin, kx, ky, kz]
+    ref = torch.nn.functional.conv3d(vol, w, padding=1).permute(0, 2, 3, 4, 1).reshape(-1, cout).numpy()
+    assert np.abs(got - ref).max() < 1e-4
+    # strided 2x2x2 convolution (offset -0.5) onto the coarse grid of calculate_grid (sparseconvnet.py:387-401)
+    k2 = rng.standard_normal((2, 2, 2, cin, cout)).astype(np.float32)
+    G2 = 4
+    ii = np.stack(np.meshgrid(np.arange(G2), np.arange(G2), np.arange(G2), indexing="ij"), -1).reshape(-1, 3)
+    pos = (ii + 0.5).astype(np.float32)
+    feat = rng.standard_normal((len(pos), cin)).astype(np.float32)
+    coarse = np.unique(ii - ii % 2, axis=0).astype(np.float32) + 0.5
+    got = O.c_sparse_conv(feat, pos, coarse, 1.0, [-0.5] * 3, k2)
+    vol = torch.from_numpy(feat).view(1, G2, G2, G2, cin).permute(0, 4, 1, 2, 3)
+    ref = torch.nn.functional.conv3d(vol, torch.from_numpy(k2).permute(4, 3, 0, 1, 2), stride=2)
+    ref = ref.permute(0, 2, 3, 4, 1).reshape(-1, cout).numpy()
+    assert np.abs(got - ref).max() < 1e-4
+    # transposed 2x2x2 back to the fine grid (DeConvolution: in = 2 * coarse position, sparseconvnet.py:643-646)
+    cf = rng.standard_normal((len(coarse), cin)).astype(np.float32)
+    up = O.c_sparse_conv(cf, coarse, pos, 1.0, [-0.5] * 3, k2, transpose=True)
+    volc = torch.from_numpy(cf).view(1, 2, 2, 2, cin).permute(0, 4, 1, 2, 3)
+    ref = torch.nn.functional.conv_transpose3d(volc, torch.from_numpy(k2).permute(3, 4, 0, 1, 2), stride=2)
+    ref = ref.permute(0, 2, 3, 4, 1).reshape(-1, cout).numpy()
+    assert np.abs(up - ref).max() < 1e-4
+
+
+def test_continuous_conv_oracle_known_answers():
+    """A spatially constant filter makes the convolution a plain sum: out = (sum_n imp_n f_n) W; nearest-neighbour
+    interpolation with the identity mapping on lattice offsets reproduces the sparse 3x3x3 convolution."""
+    from oracle import ops as O
+    rng = np.random.default_rng(2)
+    n, cin, cout = 40, 3, 5
+    pos = rng.random((n, 3)).astype(np.float32)
+    feat = rng.standard_normal((n, cin)).astype(np.float32)
+    W = rng.standard_normal((cin, cout)).astype(np.float32)
+    filt = np.broadcast_to(W, (3, 3, 3, cin, cout)).copy()
+    nbr = np.tile(np.arange(n), 2)
+    splits = np.array([0, n, 2 * n])
+    outp = np.array([[0.5, 0.5, 0.5], [0.2, 0.7, 0.1]], np.float32)
+    for mapping in (0, 1):
+        for interp in (0, 1):
+            got = O.c_continuous_conv(filt, outp, [4.0], [0, 0, 0], pos, feat, None, nbr, None, splits, True, mapping, False, interp)
+            assert np.abs(got - feat.sum(0) @ W).max() < 1e-4
+    got = O.c_continuous_conv(filt, outp, [4.0], [0, 0, 0], pos, feat, None, nbr, None, splits, True, 1, True, 1)
+    assert np.abs(got - feat.mean(0) @ W).max() < 1e-5
+    G = 4
+    ii = np.stack(np.meshgrid(np.arange(G), np.arange(G), np.arange(G), indexing="ij"), -1).reshape(-1, 3)
+    lp = (ii + 0.5).astype(np.float32)
+    lf = rng.standard_normal((len(lp), cin)).astype(np.float32)
+    k = rng.standard_normal((3, 3, 3, cin, cout)).astype(np.float32)        # sparse-conv layout [x, y, z]
+    ref = O.c_sparse_conv(lf, lp, lp, 1.0, [0, 0, 0], k)
+    idx, rs, _ = O.c_radius(lp, lp, 1.8)                                    # the 27-neighbourhood (sqrt(3) < 1.8)
+    # extent 3 voxels, align_corners: offsets {-1, 0, 1} -> p = d * 2 / 3 -> u = (p + 1) / 2 * 2 = d * 2 / 3 + 1 ... use extent 2: u = d + 1
+    got = O.c_continuous_conv(np.ascontiguousarray(k.transpose(2, 1, 0, 3, 4)), lp, [2.0], [0, 0, 0], lp, lf, None, idx, None,
+                              rs, True, 0, False, 0)
+    assert np.abs(got - ref).max() < 1e-4
