@@ -208,6 +208,10 @@ def _tc_ok(srcs):
 
 
 USE_ROW_MLP = os.environ.get("O3DML_ROW_MLP", "1") != "0"
+# one-thread-per-row layers need rows >= SMs x 256 x a few to fill the machine: below this the tensor-core kernel
+# (128 rows per CTA, K >= TC_MIN_K) has the shorter critical path (1 cloud per GPU: 11 264 rows = 44 CTAs, 25 us
+# against ~10 us; profiles/r02_launches_randlanet_1cloud.md)
+ROW_MLP_MIN_ROWS = int(os.environ.get("O3DML_ROW_MLP_MIN_ROWS", "40000"))
 
 
 def _rows_small_ok(srcs, out, ld, co):
@@ -230,7 +234,8 @@ def linear(srcs, weight, out, scale=None, shift=None, residual=None, act=None, s
     co = wt.shape[1] if out_channels is None else out_channels
     ld = (out.stride(0) if out_nchw_plane == 0 else co) if out_ld is None else out_ld
     res_ld = residual.stride(0) if residual is not None else 0
-    if (packed and USE_ROW_MLP and residual is None and out_nchw_plane == 0 and len(srcs) <= 2 and
+    prefer_tc = packed and n < ROW_MLP_MIN_ROWS and _tc_ok(srcs)
+    if (packed and USE_ROW_MLP and not prefer_tc and residual is None and out_nchw_plane == 0 and len(srcs) <= 2 and
             lib().o3dml_linear_rows_small_supported(srcs[0].channels, srcs[1].channels if len(srcs) == 2 else 0,
                                                     co) and _rows_small_ok(srcs, out, ld, co)):
         hs, ht = weight.host_affine(scale, shift)

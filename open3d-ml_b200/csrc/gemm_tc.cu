@@ -107,10 +107,7 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, 
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
+using tc::mbar_arrive_expect_tx;
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
@@ -203,11 +200,12 @@ template <int BN>
 struct GtCfg {
     static constexpr int B_BYTES = BN * 128;                       // one of hi/lo per stage
     static constexpr int STAGE = GT_A_BYTES + 2 * B_BYTES;         // raw A + W hi + W lo; multiples of 1024
-    static constexpr int STAGES = BN >= 128 ? 4 : 5;
+    // bytes in flight = L2 bandwidth x latency: at BN = 64 a slice is consumed every ~430 cycles and takes ~2 500 to
+    // arrive, i.e. ~190 KB must be outstanding (5 x 32 KB stages measured 648 cycles per slice, TMA-latency bound)
+    static constexpr int STAGES = BN >= 128 ? 4 : 6;
     static constexpr int A_COL0 = 2 * BN;                          // TMEM: accumulators first, then the A slots
     static constexpr int TMEM_COLS = 512;                          // 2 * BN + STAGES * 64 <= 512, power of two
     static_assert(2 * BN + STAGES * 64 <= 512, "TMEM budget");
-    static_assert(STAGES <= GT_FLUSH + 1, "a chunk must be folded before its TMEM buffer is reused");
     static constexpr int TAIL = GT_MAX_SRC * GT_ROWS * 8 + GT_ROWS * 8 + 2 * BN * 4 + 256;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE + TAIL + 1024;
 };
@@ -441,9 +439,10 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
         };
         for (int s = 0; s < nsl; ++s) {
             const int stage = s % S, use = s / S;
-            // a chunk whose last slice is at least S slices behind has certainly drained (its stage was reused);
-            // it is folded before slice (chunk + 2) * GT_FLUSH reuses its TMEM buffer (S - 1 <= GT_FLUSH)
-            while (next_flush < last_chunk && s >= (next_flush + 1) * GT_FLUSH + S - 1) fold(next_flush++);
+            // a chunk whose last slice is S slices behind has certainly drained (its stage was reused): fold it then,
+            // and in any case before slice (chunk + 2) * GT_FLUSH reuses its TMEM buffer (the fold waits if it must)
+            constexpr int LAG = (S - 1 < GT_FLUSH) ? S - 1 : GT_FLUSH;
+            while (next_flush < last_chunk && s >= (next_flush + 1) * GT_FLUSH + LAG) fold(next_flush++);
 #ifdef O3DML_DEBUG_TIMING
             const long long tq0 = clock64();
 #endif

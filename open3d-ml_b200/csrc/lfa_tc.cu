@@ -107,38 +107,47 @@ __device__ __forceinline__ void issue_identity(uint32_t tmem_d, const uint8_t* i
     }
 }
 
-// Same product with B streamed from global memory (host-packed images) through a 2-slot ring
-// of 32-channel slices; the copy of slice s+1 overlaps the MMAs of slice s.  Called by ALL
-// threads; returns when the accumulator is complete.  ph[] = wait parities of the ring barriers.
+// Same product with B streamed from global memory (host-packed images) through a 2-slot ring of 32-channel
+// slices.  ONE thread runs the whole stream: it hands each slice (hi + lo: two contiguous blocks of the image)
+// to the bulk-copy engine (cp.async.bulk, bytes counted on full[slot]), waits for it, issues the slice's MMAs and
+// commits them to free[slot] (ring reuse) -- the copy of slice s+1 overlaps the MMAs of slice s.  Everybody else
+// only waits for `done` (the commit after the last slice).  Round 1 copied every slice with all 256 threads
+// through registers (LDG -> STS, 256 KB per tile at d = 256) with a __syncthreads per slice: 14 % tensor-pipe
+// activity, long-scoreboard stalls (profiles/r02_lfa_ncu_full.md).
+// mb[0..1] = full, mb[2..3] = free, mb[4] = done; ph[] = this thread's wait parities of the five barriers.
 template <int N, int K>
 __device__ __forceinline__ void gemm_streamed(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo,
                                               const uint4* __restrict__ img, uint8_t* ring, int slot_bytes,
-                                              uint64_t* mb_ring, uint32_t* ph, int tid) {
+                                              uint64_t* mb, uint32_t* ph, int tid) {
     constexpr uint32_t idesc = tc::idesc_f16(LTC_ROWS, N);
     constexpr uint32_t A_LBO = LTC_ROWS * 16, B_LBO = N * 16;
     constexpr int CH = LTC_SLICE / 8;                 // 16-byte k-chunks per slice
     constexpr int SL_U4 = CH * N;                     // uint4 per slice per image
     constexpr int IMG_U4 = K / 8 * N;                 // uint4 per image (hi, then lo)
     constexpr int NSL = K / LTC_SLICE;
-    auto copy_slice = [&](int s, int slot) {
-        uint4* dst = reinterpret_cast<uint4*>(ring + (size_t)slot * slot_bytes);
-        const uint4* src_hi = img + (size_t)s * SL_U4;
-        const uint4* src_lo = img + IMG_U4 + (size_t)s * SL_U4;
-        for (int i = tid; i < SL_U4; i += LTC_THREADS) {
-            dst[i] = src_hi[i];
-            dst[SL_U4 + i] = src_lo[i];
-        }
-        tc::fence_async_smem();
-    };
-    copy_slice(0, 0);
-    tc::tc_fence_before();
-    __syncthreads();
-    tc::tc_fence_after();   // order the MMAs issued below after the barrier (operands now visible)
-    for (int s = 0; s < NSL; ++s) {
-        const int slot = s & 1;
-        if (tid == 0) {
+    constexpr uint32_t SL_BYTES = SL_U4 * 16;
+    if (tid == 0) {
+        auto copy_slice = [&](int s) {
+            const int slot = s & 1;
+            uint8_t* dst = ring + (size_t)slot * slot_bytes;
+            tc::mbar_arrive_expect_tx(&mb[slot], 2 * SL_BYTES);
+            tc::bulk_copy_g2s(dst, img + (size_t)s * SL_U4, SL_BYTES, &mb[slot]);
+            tc::bulk_copy_g2s(dst + SL_BYTES, img + IMG_U4 + (size_t)s * SL_U4, SL_BYTES, &mb[slot]);
+        };
+        copy_slice(0);
+        for (int s = 0; s < NSL; ++s) {
+            const int slot = s & 1;
+            if (s + 1 < NSL) {
+                if (s >= 1) {     // slot (s+1)&1 was read by slice s-1: wait until those MMAs are done
+                    tc::mbar_wait(&mb[2 + ((s + 1) & 1)], ph[2 + ((s + 1) & 1)]);
+                    ph[2 + ((s + 1) & 1)] ^= 1;
+                }
+                copy_slice(s + 1);
+            }
+            tc::mbar_wait(&mb[slot], ph[slot]);
+            ph[slot] ^= 1;
             const uint8_t* b_hi = ring + (size_t)slot * slot_bytes;
-            const uint8_t* b_lo = b_hi + (size_t)SL_U4 * 16;
+            const uint8_t* b_lo = b_hi + SL_BYTES;
 #pragma unroll
             for (int ks = 0; ks < LTC_SLICE / 16; ++ks) {
                 const int kc = s * CH + ks * 2;  // first k-chunk of this k-step in A
@@ -150,26 +159,20 @@ __device__ __forceinline__ void gemm_streamed(uint32_t tmem_d, const uint8_t* a_
                 tc::umma_f16(tmem_d, ah, bl, idesc, 1);
                 tc::umma_f16(tmem_d, al, bh, idesc, 1);
             }
-            tc::umma_commit(&mb_ring[slot]);
+            tc::umma_commit(&mb[2 + slot]);
         }
-        if (s + 1 < NSL) {
-            if (s >= 1) {  // slot (s+1)&1 was read by slice s-1: wait until those MMAs are done
-                tc::mbar_wait(&mb_ring[(s + 1) & 1], ph[(s + 1) & 1]);
-                ph[(s + 1) & 1] ^= 1;
-            }
-            copy_slice(s + 1, (s + 1) & 1);
+        tc::umma_commit(&mb[4]);
+        // the free[] commits of the last two slices are not waited for inside the loop: consume them here so
+        // that the parities are in step for the next call (they complete no later than `done`)
+        if (NSL >= 2) {
+            tc::mbar_wait(&mb[2 + ((NSL - 2) & 1)], ph[2 + ((NSL - 2) & 1)]);
+            ph[2 + ((NSL - 2) & 1)] ^= 1;
         }
-        tc::tc_fence_before();
-        __syncthreads();
-        tc::tc_fence_after();
+        tc::mbar_wait(&mb[2 + ((NSL - 1) & 1)], ph[2 + ((NSL - 1) & 1)]);
+        ph[2 + ((NSL - 1) & 1)] ^= 1;
     }
-    // the commits of the last two slices have not been waited for yet
-    if (NSL >= 2) {
-        tc::mbar_wait(&mb_ring[(NSL - 2) & 1], ph[(NSL - 2) & 1]);
-        ph[(NSL - 2) & 1] ^= 1;
-    }
-    tc::mbar_wait(&mb_ring[(NSL - 1) & 1], ph[(NSL - 1) & 1]);
-    ph[(NSL - 1) & 1] ^= 1;
+    tc::mbar_wait(&mb[4], ph[4]);
+    ph[4] ^= 1;
     tc::tc_fence_after();
 }
 
@@ -190,7 +193,7 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
     float* W10 = reinterpret_cast<float*>(ring + 2 * C::RING_SLOT);  // [12][H]
     float* ST2 = W10 + 12 * H;                                       // [2][H] (+ Wl2^T [H][H] for H < 16)
     uint64_t* mbar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ST2) + C::ST2_BYTES);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (LTC_ROWS - 1);   // neighbour row of the tile this thread works on
@@ -244,7 +247,7 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
     }
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tc::mbar_init(&mbar[i], 1);
+        for (int i = 0; i < 8; ++i) tc::mbar_init(&mbar[i], 1);
         tc::fence_mbar_init();
     }
     tc::fence_async_smem();
@@ -258,7 +261,7 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
     // TRANS: the lse2 accumulator aliases the score columns (it is consumed before they are written)
     constexpr int LSE2_COL = C::TRANS ? 0 : D;
     uint32_t ph_main[2] = {0, 0};  // parities of mbar[0] (lse2) and mbar[1] (scores)
-    uint32_t ph_ring[2] = {0, 0};  // parities of mbar[2], mbar[3] (weight ring)
+    uint32_t ph_ring[5] = {0, 0, 0, 0, 0};  // parities of mbar[2..6]: weight ring full / free and `done` (gemm_streamed)
 
     // TRANS kernels software-pipeline the gathers over tiles: the neighbour index of tile t+2 and the
     // coordinates / feature rows of tile t+1 are requested at the top of tile t and land while its

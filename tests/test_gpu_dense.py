@@ -194,6 +194,7 @@ def test_linear_rows_small(c0, c1, co, n, monkeypatch):
     """rowmlp.cu (weights in the kernel parameter block, thread per row) vs float64 torch; the
     second source is gathered through a batch-relative index as in the RandLA-Net decoder."""
     monkeypatch.setattr(L, "USE_ROW_MLP", True)
+    monkeypatch.setattr(L, "ROW_MLP_MIN_ROWS", 0)      # the product prefers the tensor-core kernel below 40 000 rows
     assert L.lib().o3dml_linear_rows_small_supported(c0, c1, co) == 1
     B = 2 if n > 1 else 1
     a = rnd(B * n, c0, seed=1)

@@ -7,6 +7,7 @@ import torch
 from oracle import ops as O
 from open3d_ml_b200 import synth
 import open3d_ml_b200 as M
+from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
 KITTI = dict(voxel_size=[0.16, 0.16, 4], rmin=[0, -39.68, -3], rmax=[69.12, 39.68, 1])
