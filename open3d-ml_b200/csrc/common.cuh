@@ -88,6 +88,19 @@ __device__ __forceinline__ int64_t load_index(const void* p, int64_t i, int is64
     return is64 ? ((const int64_t*)p)[i] : (int64_t)((const int32_t*)p)[i];
 }
 
+// (d0, d1) += a * (b0, b1) as ONE packed instruction (sm_100 FFMA2: `FFMA2 R, R.F32, UR.F32x2, R.F32x2` -- the scalar
+// multiplicand is broadcast, the weight pair comes from a uniform-register pair loaded from the constant bank).  Two
+// independent IEEE fp32 FMAs: bit-identical to two FFMA.  lfa16c_kernel is issue bound (73-76 % of the issue slots,
+// FMA pipe 47-50 %, profiles/r02_lfa_ncu_full.md): halving the FMA instructions of its three small products is the lever.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, float b1) {
+    uint64_t av, bv, cv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(cv) : "f"(d0), "f"(d1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cv) : "l"(av), "l"(bv));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(cv));
+}
+
 // activation codes shared with the C ABI
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {

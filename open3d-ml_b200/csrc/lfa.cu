@@ -485,7 +485,8 @@ lfa16c_kernel(const __grid_constant__ LfaParams p, const __grid_constant__ Lfa16
 #pragma unroll
             for (int q = 0; q < 10; ++q)      // weight rows are consumed contiguously -> LDCU.128
 #pragma unroll
-                for (int o = 0; o < H; ++o) r1[o] = fmaf(e[q], w.v[W16_W10 + q * H + o], r1[o]);
+                for (int o = 0; o < H; o += 2)
+                    ffma2(r1[o], r1[o + 1], e[q], w.v[W16_W10 + q * H + o], w.v[W16_W10 + q * H + o + 1]);
 #pragma unroll
             for (int o = 0; o < H; ++o) {
                 const float a = fmaf(r1[o], w.v[W16_S10 + o], w.v[W16_T10 + o]);
@@ -501,7 +502,8 @@ lfa16c_kernel(const __grid_constant__ LfaParams p, const __grid_constant__ Lfa16
 #pragma unroll
                 for (int k = 0; k < H; ++k)
 #pragma unroll
-                    for (int o = 0; o < H; ++o) r2[o] = fmaf(r1[k], w.v[W16_WL2 + k * H + o], r2[o]);
+                    for (int o = 0; o < H; o += 2)
+                        ffma2(r2[o], r2[o + 1], r1[k], w.v[W16_WL2 + k * H + o], w.v[W16_WL2 + k * H + o + 1]);
 #pragma unroll
                 for (int o = 0; o < H; ++o) {
                     const float a = fmaf(r2[o], w.v[W16_S2 + o], w.v[W16_T2 + o]);
@@ -515,7 +517,8 @@ lfa16c_kernel(const __grid_constant__ LfaParams p, const __grid_constant__ Lfa16
 #pragma unroll
         for (int k = 0; k < D; ++k)
 #pragma unroll
-            for (int c = 0; c < D; ++c) sc[c] = fmaf(x[k], w.v[W16_WS + k * D + c], sc[c]);
+            for (int c = 0; c < D; c += 2)
+                ffma2(sc[c], sc[c + 1], x[k], w.v[W16_WS + k * D + c], w.v[W16_WS + k * D + c + 1]);
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             St[c * L16_RS + tid] = sc[c];

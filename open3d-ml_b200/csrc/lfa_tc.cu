@@ -353,10 +353,10 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
             for (int q = 0; q < 10; ++q) {   // warp-uniform LDS.128 of the weights
                 const float4 wa = *reinterpret_cast<const float4*>(&W10[q * H + ch * 8]);
                 const float4 wb = *reinterpret_cast<const float4*>(&W10[q * H + ch * 8 + 4]);
-                r[0] = fmaf(e[q], wa.x, r[0]); r[1] = fmaf(e[q], wa.y, r[1]);
-                r[2] = fmaf(e[q], wa.z, r[2]); r[3] = fmaf(e[q], wa.w, r[3]);
-                r[4] = fmaf(e[q], wb.x, r[4]); r[5] = fmaf(e[q], wb.y, r[5]);
-                r[6] = fmaf(e[q], wb.z, r[6]); r[7] = fmaf(e[q], wb.w, r[7]);
+                ffma2(r[0], r[1], e[q], wa.x, wa.y);   // packed FFMA2: half the FMA instructions of the LocSE MLP
+                ffma2(r[2], r[3], e[q], wa.z, wa.w);
+                ffma2(r[4], r[5], e[q], wb.x, wb.y);
+                ffma2(r[6], r[7], e[q], wb.z, wb.w);
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
