@@ -346,8 +346,8 @@ def run_reference(args, wl):
     v = pts * args.steps / dt / 1e6
     line = dict(metric="M points/s forward", value=round(v, 5), unit="Mpoints/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=round(1e3 * dt / args.steps, 3),
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                impl="reference",
+                higher_is_better=True, scaling=("weak" if args.units else "strong"), vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
                 config=dict(workload=wl.name, sample="%d unit(s) of %d pts per step" % (sample, wl.N)),
                 cpu_baseline=dict(value=round(v, 5), unit="Mpoints/s", cores=torch.get_num_threads(),
                                   kind="port", sample="%d x %d pts, %d steps" % (sample, wl.N, args.steps)),
