@@ -74,14 +74,19 @@ def lib():
     """Loads (building first if the .so is absent and nvcc is available)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build
+        from . import build as _build
+        have_nvcc = os.path.exists(_build.NVCC)
+        if have_nvcc or not os.path.exists(LIB_PATH):
+            # build() is a cheap mtime check when the library is current: an edited csrc/ or header is never
+            # served by a stale .so; without nvcc an existing library is used as it is
             try:
                 _build.build()
             except Exception as e:  # noqa: BLE001
-                raise RuntimeError(
-                    "open3d_ml_b200: CUDA library %s is missing and could not be built (%s). "
-                    "There is no CPU fallback." % (LIB_PATH, e)) from e
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        "open3d_ml_b200: CUDA library %s is missing and could not be built (%s). "
+                        "There is no CPU fallback." % (LIB_PATH, e)) from e
+                raise
         h = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(h, name)

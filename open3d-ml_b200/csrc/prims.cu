@@ -1,5 +1,5 @@
 // prims.cu -- device-wide primitives written for this library:
-//   * exclusive scan of uint32 arrays (single-block fast path, 3-kernel path)
+//   * exclusive scan of uint32 arrays (single-block fast path, single-pass decoupled look-back above one tile)
 //   * stable LSD radix sort of (uint64 key, uint32 value) pairs, 8 bits per pass
 // Both are small-N, latency-bound steps of the voxel / hash-grid builders
 // (N = 2e4 .. 3e5 points per call), so they favour few, simple launches over
@@ -70,24 +70,23 @@ scan_single_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, i
     if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
+// Single-pass scan with decoupled look-back (one launch for any n > one tile): every block takes a tile ticket
+// (atomic counter: a block only ever waits for blocks that already hold a lower ticket, i.e. are resident or done),
+// publishes its tile aggregate, then walks back over its predecessors' 64-bit status words
+// (flag << 32 | value; flag 1 = aggregate, 2 = inclusive prefix) until it meets an inclusive prefix.
+// Replaces the single-block multi-tile loop (12 us at 40 k elements: 5 of them per voxelize call) and the
+// 3-launch path above 64 k elements.  status[0] is the ticket counter, status[1 + tile] the tile states; the caller's
+// temp buffer is zeroed by a memset node in front of the launch.
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_tile_sums(const uint32_t* __restrict__ in, int64_t n, uint32_t* __restrict__ sums) {
+scan_lookback(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n,
+              unsigned long long* __restrict__ status, uint32_t* __restrict__ total_out) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t tile_total;
-    int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-    uint32_t s = 0;
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) s += (i0 + j < n) ? in[i0 + j] : 0u;
-    block_excl_scan(s, &tile_total, warp_sums);
-    if (threadIdx.x == 0) sums[blockIdx.x] = tile_total;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS)
-scan_tiles_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n,
-                 const uint32_t* __restrict__ tile_offsets) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t tile_total;
-    int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    __shared__ uint32_t s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = (uint32_t)atomicAdd(&status[0], 1ull);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const int64_t i0 = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
     uint32_t s = 0;
 #pragma unroll
@@ -95,7 +94,30 @@ scan_tiles_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, in
         v[j] = (i0 + j < n) ? in[i0 + j] : 0u;
         s += v[j];
     }
-    uint32_t ex = block_excl_scan(s, &tile_total, warp_sums) + tile_offsets[blockIdx.x];
+    uint32_t ex = block_excl_scan(s, &tile_total, warp_sums);
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* st = status + 1;
+        const uint32_t total = tile_total;
+        uint32_t prefix = 0;
+        if (tile == 0) {
+            st[0] = (2ull << 32) | total;
+        } else {
+            st[tile] = (1ull << 32) | total;
+            __threadfence();
+            for (int64_t j = (int64_t)tile - 1; j >= 0; --j) {
+                unsigned long long w;
+                do { w = st[j]; } while ((w >> 32) == 0ull);
+                prefix += (uint32_t)w;
+                if ((w >> 32) == 2ull) break;
+            }
+            st[tile] = (2ull << 32) | (uint32_t)(prefix + total);
+        }
+        __threadfence();
+        s_prefix = prefix;
+        if (total_out && (int64_t)(tile + 1) * SCAN_TILE >= n) *total_out = prefix + total;
+    }
+    __syncthreads();
+    ex += s_prefix;
 #pragma unroll
     for (int j = 0; j < SCAN_ITEMS; ++j) {
         if (i0 + j < n) out[i0 + j] = ex;
@@ -105,7 +127,7 @@ scan_tiles_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, in
 
 size_t scan_temp_bytes(int64_t n) {
     int64_t tiles = ceil_div<int64_t>(n, SCAN_TILE);
-    return align_up((size_t)(tiles + 1) * sizeof(uint32_t));
+    return align_up((size_t)(tiles + 2) * sizeof(unsigned long long));
 }
 
 // out may alias in.  total_out (device, optional) receives the grand total.
@@ -115,15 +137,14 @@ cudaError_t exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, uin
         if (total_out) return cudaMemsetAsync(total_out, 0, sizeof(uint32_t), st);
         return cudaSuccess;
     }
-    if (n <= 16 * SCAN_TILE) {
+    if (n <= SCAN_TILE) {
         scan_single_block<<<1, SCAN_THREADS, 0, st>>>(in, out, n, total_out);
         return cudaGetLastError();
     }
-    int64_t tiles = ceil_div<int64_t>(n, SCAN_TILE);
-    uint32_t* sums = (uint32_t*)temp;
-    scan_tile_sums<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, sums);
-    scan_single_block<<<1, SCAN_THREADS, 0, st>>>(sums, sums, tiles, total_out);
-    scan_tiles_apply<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, n, sums);
+    const int64_t tiles = ceil_div<int64_t>(n, SCAN_TILE);
+    cudaError_t e = cudaMemsetAsync(temp, 0, (size_t)(tiles + 1) * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    scan_lookback<<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, out, n, (unsigned long long*)temp, total_out);
     return cudaGetLastError();
 }
 

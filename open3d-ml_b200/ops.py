@@ -131,7 +131,7 @@ def ragged_to_dense(values, row_splits, out_col_size, default_value, _add=0):
 
 def knn_search(points, queries, k, points_row_splits=None, queries_row_splits=None,
                index_dtype=torch.int32, metric="L2", ignore_query_point=False,
-               return_distances=False):
+               return_distances=False, allow_short=False):
     """open3d.ml.torch.ops.knn_search.  Rows ascend by (distance, index); distances are squared
     L2 as upstream returns them for metric='L2'."""
     if metric != "L2":
@@ -147,6 +147,12 @@ def knn_search(points, queries, k, points_row_splits=None, queries_row_splits=No
     if qs.numel() - 1 != batch:
         raise RuntimeError("knn_search: row splits disagree on the batch size")
     k = int(k)
+    # upstream returns ragged (shorter) rows when a batch item holds fewer than k points; this op returns dense
+    # [Nq, k] rows, so refuse instead of handing out -1 padded indices that a caller would gather with
+    short = int((ps[1:] - ps[:-1]).min()) if batch > 0 and q.shape[0] > 0 and not allow_short else k
+    if short < k:      # allow_short=True keeps the C-ABI behaviour: -1 / +inf padded dense rows
+        raise RuntimeError("knn_search: a batch item has %d points, fewer than k = %d (ragged results are not "
+                           "implemented)" % (short, k))
     idx = torch.empty((q.shape[0], k), dtype=index_dtype, device=dev)
     d2 = torch.empty((q.shape[0], k), dtype=torch.float32, device=dev) if return_distances else None
     wsb = L.lib().o3dml_knn_workspace_bytes(p.shape[0], q.shape[0], batch)

@@ -96,11 +96,11 @@ def test_ragged_to_dense():
     assert not out.is_cuda and np.array_equal(out.numpy(), O.np_ragged_to_dense(v64, rs, 8, -1))
 
 
-def knn_check(P, Q, k, ps=None, qs=None, dtype=torch.int32):
+def knn_check(P, Q, k, ps=None, qs=None, dtype=torch.int32, allow_short=False):
     ri, rd = O.c_knn(P, Q, k, ps, qs)
     r = M.knn_search(T(P), T(Q), k, None if ps is None else T(np.asarray(ps, np.int64)),
                      None if qs is None else T(np.asarray(qs, np.int64)), index_dtype=dtype,
-                     return_distances=True)
+                     return_distances=True, allow_short=allow_short)
     gi = r.neighbors_index.reshape(len(Q), k).cpu().numpy()
     gd = r.neighbors_distance.reshape(len(Q), k).cpu().numpy()
     assert gi.dtype == (np.int32 if dtype == torch.int32 else np.int64)
@@ -124,8 +124,10 @@ def test_knn_batched_short_items_and_duplicates():
     P = synth.uniform_cloud(3000, 4)
     P[100:110] = P[0]
     Q = synth.uniform_cloud(700, 5)
-    gi = knn_check(P, Q, 8, [0, 2000, 2005, 3000], [0, 300, 350, 700])
+    gi = knn_check(P, Q, 8, [0, 2000, 2005, 3000], [0, 300, 350, 700], allow_short=True)
     assert (gi[300:350, 5:] == -1).all()
+    with pytest.raises(RuntimeError, match="fewer than k"):        # the reference-facing op refuses ragged results
+        M.knn_search(T(P), T(Q), 8, T(np.asarray([0, 2000, 2005, 3000], np.int64)), T(np.asarray([0, 300, 350, 700], np.int64)))
     knn_check(P[:2000], P[:200], 12)
     flat = synth.uniform_cloud(5000, 6)
     flat[:, 2] = 0.25                                    # degenerate (planar) extent
