@@ -37,6 +37,7 @@
 #include "common.cuh"
 #include "tc.cuh"
 #include <cuda.h>
+#include <algorithm>
 
 namespace o3dml {
 
@@ -667,7 +668,18 @@ static int gemm_tc_launch(GemmTcParams& p, const void* wimg, cudaStream_t st) {
     O3DML_CHECK(p.Kpad % GT_KS == 0 && p.Kpad >= p.K, "linear_tc: weight image K padding must be a multiple of 32");
     O3DML_CHECK(p.Npad == 32 || p.Npad == 64 || p.Npad % 128 == 0,
                 "linear_tc: weight image rows must be padded to 32, 64 or a multiple of 128");
-    const int bn = p.Npad == 32 ? 32 : (p.Npad == 64 ? 64 : 128);
+    int bn = p.Npad == 32 ? 32 : (p.Npad == 64 ? 64 : 128);
+    if (bn == 128) {
+        // a grid that fills less than half of the SMs (PointPillars block 3: 27 x 2 CTAs; one cloud per GPU: 6 - 88)
+        // runs as 64-column tiles instead: twice the CTAs, 12 x 36 instead of 12 x 64 MMA cycles per slice each
+        int64_t row_tiles = ceil_div<int64_t>(p.N, GT_ROWS);
+        if (p.mode == 1) {
+            int best_tiles = 1 << 30;
+            for (int l = 0; l <= 7; ++l) best_tiles = std::min(best_tiles, ceil_div(p.OW, 1 << l) * ceil_div(p.OH, GT_ROWS >> l));
+            row_tiles = (p.N / ((int64_t)p.OH * p.OW)) * best_tiles;
+        }
+        if (2 * row_tiles * (p.Npad / 128) <= gt_num_sms()) bn = 64;
+    }
     {   // weight image: fp32 [2 * Npad][Kpad] (TF32 hi rows, then lo rows)
         const uint64_t dims[2] = {(uint64_t)p.Kpad, (uint64_t)2 * p.Npad};
         const uint64_t str[1] = {(uint64_t)p.Kpad * 4};
