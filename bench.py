@@ -378,6 +378,29 @@ def timed_region(fn, steps, dist_on, dev):
     return ms
 
 
+def pin_to_gpu_numa_node(local):
+    """Binds this rank's host threads to the cores of the NUMA node its GPU hangs off (the pinned-host -> device copies
+    of the e2e region cross the inter-socket link otherwise: round-1 e2e scaling 0.90 at 8 GPUs).  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                    # 0000:1b:00.0
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def ev_time_ms(fn, reps=5, warm=2):
     """Mean device time of fn() over reps, CUDA events on the current stream."""
     for _ in range(warm):
@@ -414,6 +437,7 @@ def run_b200(args, wl):
     dist_on = world > 1
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = pin_to_gpu_numa_node(local) if dist_on else None
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -664,7 +688,8 @@ def run_b200(args, wl):
                                         "post-batch all_gather of per-frame results in the e2e region" % (world, scaling),
                             l2="inputs + activations per step (%.0f MB inputs) exceed the 126 MB L2; no flush"
                                % (bi / 1e6),
-                            launch="forward replayed from a CUDA graph" if graphed or dense_timers else "eager launches"),
+                            launch="forward replayed from a CUDA graph" if graphed or dense_timers else "eager launches",
+                            numa_node_rank0=numa),
                 clocks=clk, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu, **extra)
     emit(line)
     if dist_on:

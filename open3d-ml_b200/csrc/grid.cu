@@ -15,6 +15,7 @@
 #include "../../include/o3dml_b200.h"
 #include "prims.cuh"
 #include <float.h>
+#include <stdlib.h>
 
 namespace o3dml {
 
@@ -87,7 +88,7 @@ __global__ void grid_bbox_kernel(const float* __restrict__ pts, int64_t n,
 // caller can size the cell arrays without a device->host sync.
 __global__ void grid_setup_kernel(const unsigned* __restrict__ bbox,
                                   const int64_t* __restrict__ splits, int batch, float fixed_cs,
-                                  int k, GridInfo* __restrict__ info, uint32_t* total_cells) {
+                                  int k, float knn_cell_scale, GridInfo* __restrict__ info, uint32_t* total_cells) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     uint32_t base = 0;
     for (int b = 0; b < batch; ++b) {
@@ -110,10 +111,7 @@ __global__ void grid_setup_kernel(const unsigned* __restrict__ bbox,
                 float kk = (float)(k < 4 ? 4 : k);
                 float cs2 = sqrtf(kk * e0 * e1 / (3.14159265f * (float)nb));
                 float cs3 = cbrtf(kk * e0 * e1 * e2 / (4.18879f * (float)nb));
-                // 1.3 x the radius expected to hold k points: the k-th neighbour then lies inside the r = 1 shell for almost
-                // every query (at 1.0 x about half of them walked the 125-cell r = 2 shell as well, with the lanes of a
-                // warp diverging between the two)
-                cs = fmaxf(1.3f * fmaxf(cs2, cs3), 1e-6f);
+                cs = fmaxf(knn_cell_scale * fmaxf(cs2, cs3), 1e-6f);
             }
             const double cap = 2.0 * (double)nb + 64.0;
             for (int it = 0; it < 64; ++it) {
@@ -202,31 +200,6 @@ __device__ __forceinline__ bool nb_less(float da, int ia, float db, int ib) {
 }
 
 // ------------------------------------------------------------------- k-NN ----
-// Thread per query, lanes = consecutive queries in cell order.  The per-candidate cost of the round-1 kernel was the
-// sorted insertion: ~100 predicated instructions that the whole warp executes whenever ANY lane inserts, and with 32
-// lanes some lane nearly always does (1.1 ms for the 360 k-point level of the RandLA-Net pyramid, 55-110 k warp
-// instructions per warp).  Now a candidate that beats the lane's current k-th best is only appended to a small per-lane
-// buffer in shared memory (2 instructions); the buffers are merged into the register-resident sorted lists by the lanes
-// that are converged at the end of a cell (opportunistic __activemask() collective: no lane can be waited for that
-// skipped the cell), so that the insertion code runs with all lanes busy, ~15 times per warp instead of ~300.
-constexpr int KNN_BUF = 8;        // buffered candidates per lane
-constexpr int KNN_FLUSH_AT = 5;   // collective merge when any converged lane holds this many
-
-template <int KMAX>
-__device__ __forceinline__ void knn_insert(float (&bd)[KMAX], int (&bi)[KMAX], float d, int id) {
-    if (nb_less(d, id, bd[KMAX - 1], bi[KMAX - 1])) {
-        bd[KMAX - 1] = d;
-        bi[KMAX - 1] = id;
-#pragma unroll
-        for (int j = KMAX - 1; j > 0; --j) {
-            if (nb_less(bd[j], bi[j], bd[j - 1], bi[j - 1])) {
-                float td = bd[j]; bd[j] = bd[j - 1]; bd[j - 1] = td;
-                int ti = bi[j]; bi[j] = bi[j - 1]; bi[j - 1] = ti;
-            }
-        }
-    }
-}
-
 template <int KMAX>
 __global__ void __launch_bounds__(128)
 knn_kernel(const float* __restrict__ queries, int64_t nq, const int64_t* __restrict__ qsplits,
@@ -234,9 +207,6 @@ knn_kernel(const float* __restrict__ queries, int64_t nq, const int64_t* __restr
            const GridInfo* __restrict__ info, const uint32_t* __restrict__ cell_start,
            const float4* __restrict__ sorted, int k, void* __restrict__ out_idx, int idx_is64,
            float* __restrict__ out_d2) {
-    constexpr bool BUFFERED = KMAX >= 8;
-    __shared__ float sbd[BUFFERED ? KNN_BUF * 128 : 1];
-    __shared__ int sbi[BUFFERED ? KNN_BUF * 128 : 1];
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nq) return;
     const int64_t qi = order ? (int64_t)order[t] : t;
@@ -247,12 +217,6 @@ knn_kernel(const float* __restrict__ queries, int64_t nq, const int64_t* __restr
     int bi[KMAX];
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) { bd[j] = FLT_MAX; bi[j] = 0x7fffffff; }
-    int nbuf = 0;
-    auto flush = [&]() {     // merge this lane's buffered candidates (executed by all lanes that are converged here)
-#pragma unroll 1
-        for (int u = 0; u < nbuf; ++u) knn_insert<KMAX>(bd, bi, sbd[u * 128 + threadIdx.x], sbi[u * 128 + threadIdx.x]);
-        nbuf = 0;
-    };
     const int64_t nsup = psplits[b + 1] - psplits[b];
     const int kk = (int)(nsup < k ? nsup : k);  // neighbours that exist
     if (kk > 0) {
@@ -272,31 +236,27 @@ knn_kernel(const float* __restrict__ queries, int64_t nq, const int64_t* __restr
                         if (x < 0 || x >= g.dx) continue;
                         const uint32_t c = cell_id(g, x, y, z);
                         const uint32_t s = cell_start[c], e = cell_start[c + 1];
-                        uint32_t pi = s;
-                        do {      // a cell is consumed in runs that end when this lane's buffer is full
-                            for (; pi < e && (!BUFFERED || nbuf < KNN_BUF); ++pi) {
-                                const float4 pt = sorted[pi];
-                                const float d = sqdist3(qx, qy, qz, pt.x, pt.y, pt.z);
-                                const int id = __float_as_int(pt.w);
-                                if (BUFFERED) {
-                                    if (nb_less(d, id, bd[KMAX - 1], bi[KMAX - 1])) {
-                                        sbd[nbuf * 128 + threadIdx.x] = d;
-                                        sbi[nbuf * 128 + threadIdx.x] = id;
-                                        ++nbuf;
+                        for (uint32_t pi = s; pi < e; ++pi) {
+                            const float4 pt = sorted[pi];
+                            const float d = sqdist3(qx, qy, qz, pt.x, pt.y, pt.z);
+                            const int id = __float_as_int(pt.w);
+                            if (nb_less(d, id, bd[KMAX - 1], bi[KMAX - 1])) {
+                                // replace the current worst (slot KMAX-1 holds the worst because
+                                // unused slots are +inf) and bubble it up
+                                bd[KMAX - 1] = d;
+                                bi[KMAX - 1] = id;
+#pragma unroll
+                                for (int j = KMAX - 1; j > 0; --j) {
+                                    if (nb_less(bd[j], bi[j], bd[j - 1], bi[j - 1])) {
+                                        float td = bd[j]; bd[j] = bd[j - 1]; bd[j - 1] = td;
+                                        int ti = bi[j]; bi[j] = bi[j - 1]; bi[j - 1] = ti;
                                     }
-                                } else {
-                                    knn_insert<KMAX>(bd, bi, d, id);
                                 }
                             }
-                            if (BUFFERED) {
-                                const unsigned m = __activemask();
-                                if (__any_sync(m, nbuf >= KNN_FLUSH_AT)) flush();
-                            }
-                        } while (pi < e);
+                        }
                     }
                 }
             }
-            if (BUFFERED) flush();
             // everything closer than r*cs has been seen (cells are >= cs wide, the query sits
             // inside its own cell or outside the grid on the far side); 1e-4 relative slack
             // covers the float rounding of the cell assignment
@@ -423,7 +383,13 @@ static int grid_build(const float* pts, int64_t np, const int64_t* psplits, cons
     const int T = 256;
     grid_init_kernel<<<ceil_div(batch * 6, T), T, 0, st>>>(g.bbox, batch);
     if (np > 0) grid_bbox_kernel<<<(unsigned)ceil_div<int64_t>(np, T), T, 0, st>>>(pts, np, psplits, batch, g.bbox);
-    grid_setup_kernel<<<1, 32, 0, st>>>(g.bbox, psplits, batch, fixed_cs, k, g.info, g.total_cells);
+    // cell edge of the k-NN grid relative to the radius expected to hold k points (O3DML_KNN_CELL_SCALE: tuning hook)
+    static const float cell_scale = [] {
+        const char* e = getenv("O3DML_KNN_CELL_SCALE");
+        const float v = e ? (float)atof(e) : 1.0f;
+        return v > 0.1f && v < 10.f ? v : 1.0f;
+    }();
+    grid_setup_kernel<<<1, 32, 0, st>>>(g.bbox, psplits, batch, fixed_cs, k, cell_scale, g.info, g.total_cells);
     O3DML_CUDA(cudaMemsetAsync(g.cell_start, 0, (g.max_cells + 1) * 4, st));
     O3DML_CUDA(cudaMemsetAsync(g.cursor, 0, (g.max_cells + 1) * 4, st));
     if (np > 0) grid_count_kernel<<<(unsigned)ceil_div<int64_t>(np, T), T, 0, st>>>(pts, np, psplits, batch, g.info, g.cell_of, g.cell_start);
