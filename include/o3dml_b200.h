@@ -302,6 +302,20 @@ O3DML_API int o3dml_randla_lfa_pool_tc(int stage, int d, const float* coords, co
                                        const float* s2, const float* t2, const void* wscore_image,
                                        float* agg, void* stream);
 
+/* The per-point tail of RandLA-Net in one kernel: last decoder SharedMLP on [skip | nearest_interpolation(x)]
+ * (randlanet.py:284-292, 329-350) + the fc1 classifier stack (randlanet.py:110-113, 294-298), four dense layers
+ * 32+32 -> 32 -> 64 -> 32 -> classes chained through tensor memory (tcgen05 kind::tf32, 3xTF32).
+ * weight_image: 57 344-byte device image of the four weights (open3d_ml_b200._lib.pack_tail_image: per layer and
+ * 32-wide k-chunk, TF32 hi tiles then lo tiles of [N][32] floats, K-major SWIZZLE_128B); h_scale / h_shift: HOST float
+ * [4][64] folded BN scale / shift (+ bias) per layer; LeakyReLU(slope) after the first three layers.
+ * interp_index [num_rows] (int32 / int64, batch-relative when out_rows_per_batch > 0).  out [num_rows, classes]. */
+O3DML_API int o3dml_randla_tail_supported(int skip_channels, int coarse_channels, int c1, int c2, int c3, int classes);
+O3DML_API int o3dml_randla_tail(const float* skip, int skip_ld, const float* coarse, int coarse_ld,
+                                int64_t coarse_rows, const void* interp_index, int index_is64,
+                                int64_t out_rows_per_batch, int64_t src_rows_per_batch, int64_t num_rows,
+                                const void* weight_image, const float* h_scale, const float* h_shift, float slope,
+                                int classes, float* out, void* stream);
+
 /* out[n, :] = max_j src[index[n, j], :]  -- RandLANet.random_sample (randlanet.py:300-327),
  * KPConv max_pool (kpconv.py:840-858, shadow_zero = 1), k = 1: nearest_interpolation /
  * closest_pool. */

@@ -62,6 +62,8 @@ _SIGNATURES = {
     "o3dml_linear_rows_small": (I, [L, P, I, P, P, P, I, F, P, I, I, P]),
     "o3dml_randla_lfa16_pool": (I, [I, P, P, I, I, P, L, L, P, P, P]),
     "o3dml_randla_lfa_pool_tc": (I, [I, I, P, P, I, I, P, L, L, P, P, P, P, P, P, P, P, P, P]),
+    "o3dml_randla_tail_supported": (I, [I, I, I, I, I, I]),
+    "o3dml_randla_tail": (I, [P, I, P, I, L, P, I, L, L, L, P, P, P, F, I, P, P]),
     "o3dml_gather_max": (I, [P, L, I, I, P, I, L, I, L, L, I, P, I, P]),
     "o3dml_kpconv_gather": (I, [P, L, P, L, P, I, I, P, I, P, I, F, P, P]),
     "o3dml_tc_gemm_test": (I, [P, P, P, I, I, I, P]),
@@ -155,6 +157,36 @@ def pack_tf32_image_host(w_nk):
     hi = tf32_round(w)
     lo = tf32_round(w - hi)
     return torch.cat([hi, lo], 0).contiguous()
+
+
+def _sw128_tile(b_n32):
+    """fp32 [N, 32] (one 128-byte row per output channel) -> the same tile in the K-major SWIZZLE_128B shared-memory
+    layout: 16-byte chunk c of row n sits at chunk position c ^ (n & 7)."""
+    n = b_n32.shape[0]
+    t = b_n32.reshape(n, 8, 4)
+    out = torch.empty_like(t)
+    rows = torch.arange(n)
+    for c in range(8):
+        out[rows, c ^ (rows & 7)] = t[:, c]
+    return out.reshape(n, 32)
+
+
+def pack_tail_image(weights_kn, n_pads):
+    """rl_tail.cu weight image: for every layer ([K, N] fp32, in x out) the TF32 hi tiles of its 32-wide k-chunks, then the
+    lo tiles, each [n_pad][32] floats in the SWIZZLE_128B layout; layers concatenated."""
+    parts = []
+    for w, n_pad in zip(weights_kn, n_pads):
+        w = w.detach().to(torch.float32).cpu()
+        k, n = w.shape
+        assert k % 32 == 0 and n <= n_pad
+        b = torch.zeros((n_pad, k), dtype=torch.float32)
+        b[:n] = w.t()
+        hi = tf32_round(b)
+        lo = tf32_round(b - hi)
+        for img in (hi, lo):
+            for c in range(k // 32):
+                parts.append(_sw128_tile(img[:, 32 * c:32 * c + 32].contiguous()).reshape(-1))
+    return torch.cat(parts).contiguous()
 
 
 class PackedWeight:

@@ -123,6 +123,22 @@ class RandLANetB200:
         self.num_classes = sd["fc1.3.conv.weight"].shape[0]
         self.in_channels = sd["fc0.weight"].shape[1]
         self._buf = {}
+        # ---- fused tail (rl_tail.cu): last decoder layer + fc1 stack chained through tensor memory
+        self.use_tail = os.environ.get("O3DML_RL_TAIL", "1") != "0"
+        self.tail = None
+        pl = "decoder.%d" % (num_layers - 1)
+        wd = sd[pl + ".conv.weight"][:, :, 0, 0]                          # ConvTranspose2d [in, out]
+        w0, w1, w3 = (sd["fc1.%d.conv.weight" % j][:, :, 0, 0].t() for j in (0, 1, 3))
+        skip_c = 2 * self.d_out[0]
+        if self.use_tail and L.lib().o3dml_randla_tail_supported(skip_c, wd.shape[0] - skip_c, wd.shape[1], w0.shape[1],
+                                                                 w1.shape[1], self.num_classes):
+            img = L.pack_tail_image([wd, w0, w1, w3], [32, 64, 32, 32]).to(dev)
+            sc, sh = torch.ones(4, 64), torch.zeros(4, 64)
+            for li, name in enumerate((pl, "fc1.0", "fc1.1")):
+                s_, t_ = _fold_bn(sd, name + ".batch_norm", sd[name + ".conv.bias"])
+                sc[li, :s_.numel()], sh[li, :t_.numel()] = s_, t_
+            sh[3, :self.num_classes] = sd["fc1.3.conv.bias"]
+            self.tail = (img, sc.contiguous(), sh.contiguous())
 
     # ------------------------------------------------------------------ buffers
     def _get(self, name, rows, ch):
@@ -223,10 +239,20 @@ class RandLANetB200:
         nlast = skips[-1][1]
         x = self._mlp("mlp", [L.make_src(x)], self._get("mlp", x.shape[0], x.shape[1]))
         ncoarse = nlast
+        use_tail = self.tail is not None and taps is None
         for i in range(self.num_layers):
             skip, nup = skips[-i - 2]
             interp = inp["interp_idx"][-i - 1]  # [B, nup, 1] ids into the coarse level
             p = "decoder.%d" % i
+            if use_tail and i == self.num_layers - 1:
+                img, sc, sh = self.tail
+                logits = torch.empty((B * nup, self.num_classes), dtype=torch.float32, device=self.device)
+                iv = interp.view(-1)
+                L.check(L.lib().o3dml_randla_tail(
+                    L.ptr(skip), skip.stride(0), L.ptr(x), x.stride(0), x.shape[0], L.ptr(iv),
+                    1 if iv.dtype == torch.int64 else 0, nup, ncoarse, B * nup, L.ptr(img), sc.data_ptr(), sh.data_ptr(),
+                    0.2, self.num_classes, L.ptr(logits), L.stream()))
+                return logits.view(B, N0, self.num_classes)
             cout = self.w[p + ".wt"].shape[1]
             out = self._get(p, B * nup, cout)
             self._mlp(p, [L.make_src(skip),

@@ -265,3 +265,28 @@ def test_randlanet_five_level_config_vs_golden_reference():
     # the device-side pyramid honours the per-level ratios
     got = net.forward_points(inp["coords"][0], torch.from_numpy(g["extra_feat"]))
     assert rel_err(got, g["logits"]) < TOL
+
+
+def test_randlanet_fused_tail_matches_the_layerwise_path():
+    """rl_tail.cu (last decoder layer + fc1 stack chained through tensor memory) against the four separate launches,
+    on reference-shaped inputs (int64 batch-relative interp_idx, ragged last tile) and on the device pyramid."""
+    sd, _ = H.state_dict("randlanet_semantickitti.manifest.json", 6)
+    net = M.RandLANetB200(sd)
+    assert net.tail is not None
+    B, N = 3, 4096 + 64 * 3            # not a multiple of 128 per cloud: exercises the row tail
+    inp = H.randla_inputs(B, N, 120)
+    fused = net(inp).clone()
+    n0 = M._lib.lib().o3dml_launch_count()
+    net(inp)
+    fused_launches = M._lib.lib().o3dml_launch_count() - n0
+    tail, net.tail = net.tail, None
+    n0 = M._lib.lib().o3dml_launch_count()
+    ref = net(inp).clone()
+    assert M._lib.lib().o3dml_launch_count() - n0 == fused_launches + 3      # four launches became one
+    net.tail = tail
+    assert rel_err(fused, ref) < 1e-5, rel_err(fused, ref)
+    with torch.no_grad():
+        port = MT.randlanet_forward(sd, inp)
+    assert rel_err(fused, port) < TOL
+    pts = inp["coords"][0].cuda()
+    assert torch.equal(net.forward_points(pts), fused)
