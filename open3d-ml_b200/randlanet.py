@@ -351,11 +351,16 @@ class RandLANetB200:
         key = (name,) + tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in tensors)
         ent = self._graphs.get(key)
         if ent is None:
+            import os
+            legacy = os.environ.get("O3DML_GRAPH_LEGACY") == "1"      # debugging hook: the round-2 first version
             thunk()                                        # sizes the cached buffers, sets kernel attributes
-            torch.cuda.current_stream().synchronize()
+            if legacy:
+                torch.cuda.current_stream().synchronize()
+            else:
+                torch.cuda.synchronize(self.device)        # nothing of this device in flight while capturing
             graph = torch.cuda.CUDAGraph()
             n0 = L.lib().o3dml_launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="global" if legacy else "thread_local"):
                 out = thunk()
             if len(self._graphs) > 8:
                 self._graphs.clear()

@@ -39,7 +39,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
@@ -534,9 +534,7 @@ def run_b200(args, wl):
         lfa_ms_in_step = e0.elapsed_time(e1)
     # --- e2e A: the reference-facing call (host input pytree as the reference's dataloader delivers it)
     from open3d_ml_b200 import PipelinedRunner
-    gather_on = [False]
-    base = model.forward_graphed if graphed else model
-    fwd = lambda d: with_gather(base(d)) if gather_on[0] else base(d)   # noqa: E731
+    fwd = (lambda d: with_gather(model.forward_graphed(d))) if graphed else (lambda d: with_gather(model(d)))
     runner = PipelinedRunner(fwd, dev)
 
     def e2e_stream(run, inp, n):
@@ -546,20 +544,13 @@ def run_b200(args, wl):
             acc += float(r0.view(-1)[0])          # the caller touches every result on the host
         return acc
 
-    # first pass without the collective: the CUDA graphs of both input slots are captured while no NCCL work is in
-    # flight (capturing with a collective of the previous batch still running faulted on 2 of 4 ranks at N = 4)
-    e2e_stream(runner, host_inp, 2)
-    torch.cuda.synchronize(dev)
-    if dist_on:
-        dist.barrier()
-    gather_on[0] = True
     e2e_stream(runner, host_inp, max(3, args.warmup // 2))
     ms_e2e = timed_region(lambda: e2e_stream(runner, host_inp, args.steps), 1, dist_on, dev)
     out_host = None
 
     def step_e2e_sync():
         nonlocal out_host
-        out = with_gather(model(host_inp))       # eager (no graph): plain synchronous call   # H2D of every input inside the model call (randlanet.py:254-264)
+        out = with_gather(model(host_inp))   # H2D of every input inside the model call (randlanet.py:254-264)
         outs = out if isinstance(out, (tuple, list)) else (out,)
         if out_host is None:
             out_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
@@ -580,15 +571,8 @@ def run_b200(args, wl):
     extra = {}
     if is_rl:
         pts_host = dict(points=pin(host_inp["coords"][0].clone()))
-        gather_on[0] = False
-        fwd_pts = lambda d: (with_gather(model.forward_points_graphed(d["points"])) if gather_on[0]   # noqa: E731
-                             else model.forward_points_graphed(d["points"]))
+        fwd_pts = lambda d: with_gather(model.forward_points_graphed(d["points"]))   # noqa: E731
         runner_p = PipelinedRunner(fwd_pts, dev)
-        e2e_stream(runner_p, pts_host, 2)
-        torch.cuda.synchronize(dev)
-        if dist_on:
-            dist.barrier()
-        gather_on[0] = True
         e2e_stream(runner_p, pts_host, max(3, args.warmup // 2))
         ms_p = timed_region(lambda: e2e_stream(runner_p, pts_host, args.steps), 1, dist_on, dev)
         e2e_modes["points_only"] = dict(
