@@ -18,16 +18,32 @@ def shard_bounds(num_items, rank, world_size):
     return lo, min(lo + per, num_items)
 
 
+_GATHER_BUFFERS = {}
+
+
 def gather_frame_results(local, num_items, group=None):
     """local: [n_local, ...] tensor of per-frame results of this rank's shard.  Returns the
-    [num_items, ...] tensor of all frames on every rank (pads ragged tails internally)."""
+    [num_items, ...] tensor of all frames on every rank (ragged tails are zero-padded internally).
+    One all_gather_into_tensor on persistent buffers (cached per shape): nothing is allocated or freed
+    around the collective after the first call, and the result is a view of the cached buffer -- valid until
+    the next call with the same shape."""
     world = dist.get_world_size(group)
     per = (num_items + world - 1) // world
-    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[:local.shape[0]] = local
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad, group=group)
-    return torch.cat(out, 0)[:num_items]
+    key = (tuple(local.shape[1:]), local.dtype, str(local.device), per, world, id(group))
+    buf = _GATHER_BUFFERS.get(key)
+    if buf is None:
+        if len(_GATHER_BUFFERS) > 16:
+            _GATHER_BUFFERS.clear()
+        pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        buf = _GATHER_BUFFERS[key] = (pad, out)
+    pad, out = buf
+    n = local.shape[0]
+    pad[:n].copy_(local)
+    if n < per:
+        pad[n:].zero_()
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return out[:num_items]
 
 
 def reduce_confusion(conf, group=None):
