@@ -336,17 +336,6 @@ O3DML_API int o3dml_kpconv_gather(const float* query_points, int64_t num_queries
                         int num_kernel_points, float kp_extent, float* weighted_features,
                         void* stream);
 
-/* ------------------------------------------------------------ bring-up ---- */
-
-/* tcgen05 regression hook: d[128, n] = a[128, k] * b[n, k]^T on the tensor cores with the
- * 3xFP16 split used by the fused kernels (terms = 1: hi*hi only).  One CTA; n, k multiples of 16. */
-O3DML_API int o3dml_tc_gemm_test(const float* a, const float* b, float* d, int n, int k, int terms,
-                                 void* stream);
-
-/* tcgen05 issue-rate probe (profiling aid): reps x 6 MMAs of M=128 x N x K=16; out[0] = total cycles,
- * out[1] = cycles spent issuing. */
-O3DML_API int o3dml_tc_mma_rate(int n, int reps, long long* out, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -66,10 +66,13 @@ _SIGNATURES = {
     "o3dml_randla_tail": (I, [P, I, P, I, L, P, I, L, L, L, P, P, P, F, I, P, P]),
     "o3dml_gather_max": (I, [P, L, I, I, P, I, L, I, L, L, I, P, I, P]),
     "o3dml_kpconv_gather": (I, [P, L, P, L, P, I, I, P, I, P, I, F, P, P]),
+}
+EXPORTS = tuple(_SIGNATURES)           # the product ABI: exactly what include/o3dml_b200.h declares
+# bring-up / profiling hooks (include/o3dml_b200_bringup.h): exported by the library, not part of the product ABI
+_BRINGUP_SIGNATURES = {
     "o3dml_tc_gemm_test": (I, [P, P, P, I, I, I, P]),
     "o3dml_tc_mma_rate": (I, [I, I, P, P]),
 }
-EXPORTS = tuple(_SIGNATURES)
 
 
 def lib():
@@ -90,7 +93,7 @@ def lib():
                         "There is no CPU fallback." % (LIB_PATH, e)) from e
                 raise
         h = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in _SIGNATURES.items():
+        for name, (res, args) in list(_SIGNATURES.items()) + list(_BRINGUP_SIGNATURES.items()):
             fn = getattr(h, name)
             fn.restype, fn.argtypes = res, args
         if h.o3dml_abi_version() != ABI_VERSION:

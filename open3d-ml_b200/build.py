@@ -27,7 +27,8 @@ def sources():
 
 
 def _newest_dep():
-    t = os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "o3dml_b200.h"))
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    t = max(os.path.getmtime(os.path.join(inc, f)) for f in os.listdir(inc))
     for f in os.listdir(CSRC):
         t = max(t, os.path.getmtime(os.path.join(CSRC, f)))
     return t

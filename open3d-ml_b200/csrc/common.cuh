@@ -36,7 +36,26 @@ extern "C" void o3dml_count_launches(int n);  // kernels enqueued (bench.py gpu_
 
 namespace o3dml {
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (fallback when the attribute query fails)
+
+// The opt-in dynamic shared-memory size is a per-device function attribute: `static bool configured` guards set it on
+// the first device only, so a process that drives two GPUs failed on the second.  One bit per device ordinal.
+struct PerDeviceOnce {
+    unsigned long long mask = 0;
+    bool need(int dev) const { return dev < 0 || dev >= 64 || !((mask >> dev) & 1ull); }
+    void done(int dev) { if (dev >= 0 && dev < 64) mask |= 1ull << dev; }
+};
+inline int current_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+inline int device_sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        n > 0)
+        return n;
+    return kNumSMs;
+}
 
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) {

@@ -266,11 +266,12 @@ template <int D, int STAGE>
 static int lfa_launch(const LfaParams& p, cudaStream_t st) {
     using C = LfaCfg<D>;
     const size_t smem = C::smem_bytes(STAGE);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    const int dev = current_device();
+    if (once.need(dev)) {
         O3DML_CUDA(cudaFuncSetAttribute(lfa_pool_kernel<D, STAGE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        once.done(dev);
     }
     const unsigned blocks = (unsigned)ceil_div<int64_t>(p.total, C::P);
     lfa_pool_kernel<D, STAGE><<<blocks, LFA_THREADS, smem, st>>>(p);

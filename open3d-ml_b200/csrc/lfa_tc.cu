@@ -556,17 +556,18 @@ template <int D, int STAGE>
 static int lfa_tc_launch(const LfaTcParams& p, cudaStream_t st) {
     using C = LtcCfg<D, STAGE>;
     static_assert(C::SMEM <= 227 * 1024, "shared memory budget");
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    const int dev = current_device();
+    if (once.need(dev)) {
         O3DML_CUDA(cudaFuncSetAttribute(lfa_pool_tc_kernel<D, STAGE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        configured = true;
+        once.done(dev);
     }
     int per_sm = (int)(224 * 1024 / (C::SMEM + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm * C::TMEM_COLS > 512) per_sm = 512 / C::TMEM_COLS;
     if (per_sm > 4) per_sm = 4;
-    int64_t grid = (int64_t)kNumSMs * per_sm;
+    int64_t grid = (int64_t)device_sm_count() * per_sm;
     if (grid > p.num_tiles) grid = p.num_tiles;
     lfa_pool_tc_kernel<D, STAGE><<<(unsigned)grid, C::NTH, C::SMEM, st>>>(p);
     O3DML_LAUNCH_CHECK();

@@ -3,7 +3,7 @@
 // laid out in shared memory by the CTA itself (exactly what the fused kernels do).
 // Exposed through the C ABI (o3dml_tc_gemm_test) so that tests/test_gpu_tc.py can pin the
 // descriptor encodings against torch.
-#include "../../include/o3dml_b200.h"
+#include "../../include/o3dml_b200_bringup.h"
 #include "common.cuh"
 #include "tc.cuh"
 

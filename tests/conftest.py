@@ -34,3 +34,16 @@ def rel_err(a, b):
     import torch
     a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def elem_err(a, b, q=0.999, floor=1e-3):
+    """Element-wise companion of rel_err: the q-quantile of |a-b| / (|b| + floor * max|b|).  rel_err is relative to the
+    tensor scale, so a regression confined to small-magnitude entries (logits near zero) cannot move it; here every
+    element is judged against its own magnitude down to `floor` of the scale."""
+    import torch
+    a, b = torch.as_tensor(a).double().cpu().reshape(-1), torch.as_tensor(b).double().cpu().reshape(-1)
+    scale = b.abs().max().clamp_min(1e-30)
+    r = (a - b).abs() / (b.abs() + floor * scale)
+    if r.numel() > 4_000_000:                      # torch.quantile is limited to 16 M elements; sample evenly
+        r = r[:: r.numel() // 4_000_000 + 1]
+    return float(torch.quantile(r, q))

@@ -11,7 +11,7 @@ import torch
 from oracle import models_torch as MT, ops as O
 from open3d_ml_b200 import synth
 import open3d_ml_b200 as M
-from conftest import rel_err
+from conftest import rel_err, elem_err
 import helpers as H
 
 pytestmark = pytest.mark.gpu
@@ -31,6 +31,7 @@ def test_randlanet_vs_golden_reference():
         assert rel_err(taps["encoder.%d" % i], g["tap.encoder.%d" % i]) < TOL, i
     assert out.shape == g["logits"].shape
     assert rel_err(out, g["logits"]) < TOL
+    assert elem_err(out, g["logits"]) < 1e-2      # no regression hiding in the small-magnitude logits
     assert torch.equal(out.argmax(-1).cpu(), torch.from_numpy(g["logits"]).argmax(-1))
 
 
@@ -290,3 +291,34 @@ def test_randlanet_fused_tail_matches_the_layerwise_path():
     assert rel_err(fused, port) < TOL
     pts = inp["coords"][0].cuda()
     assert torch.equal(net.forward_points(pts), fused)
+
+
+# ------------------------------------------------------------------ BASELINE sizes (configs[3], configs[4])
+def test_kpfcnn_full_size_vs_port():
+    """KPFCNN at the BASELINE configs[3] cloud size (65 536 points per cloud, S3DIS config; two clouds bound the CPU
+    port's time): batch built on the device (kpconv.build_batch), fused forward against the torch port on the SAME
+    index tensors."""
+    from open3d_ml_b200.kpconv import build_batch
+    sd, extra = H.state_dict("kpconv_s3dis.manifest.json", 5)
+    cfg = extra["cfg"]
+    clouds = [synth.room_cloud(65536, 200 + i) for i in range(2)]
+    b = build_batch(clouds, cfg)
+    net = M.KPFCNNB200(sd, cfg)
+    out = net(b)
+    tb = {k: ([t.cpu() for t in v] if isinstance(v, list) else v.cpu()) for k, v in b.items() if k != "lengths"}
+    with torch.no_grad():
+        ref = MT.kpfcnn_forward(sd, tb, cfg)
+    assert out.shape == ref.shape == (2 * 65536, ref.shape[1])
+    assert rel_err(out, ref) < TOL and elem_err(out, ref) < 1e-2
+
+
+def test_pointpillars_waymo_full_frame_vs_port():
+    """PointPillars at the BASELINE configs[4] frame size (180 000 points, 468 x 468 BEV)."""
+    sd, extra = H.state_dict("pointpillars_waymo.manifest.json", 11)
+    frames = [torch.from_numpy(synth.lidar_frame(180000, 77, synth.WAYMO_RANGE))]
+    net = M.PointPillarsB200(sd, extra["cfg"])
+    outs = net(frames)
+    with torch.no_grad():
+        ref = MT.pointpillars_forward(sd, frames, extra["cfg"])
+    for o, r in zip(outs, ref):
+        assert o.shape == r.shape and rel_err(o, r) < TOL
