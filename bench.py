@@ -134,7 +134,7 @@ def to_dev(x, dev):
 
 # ----------------------------------------------------------------------------- workloads
 class RandLAWorkload:
-    name = "RandLA-Net forward, SemanticKITTI-shaped batch (8 x 45 056 pts per GPU), BASELINE configs[2]"
+    name = "RandLA-Net forward, SemanticKITTI-shaped batch (clouds of 45 056 pts; total_units below), BASELINE configs[2]"
     short = "randlanet_semantickitti_8x45056"
     manifest = "randlanet_semantickitti.manifest.json"
 

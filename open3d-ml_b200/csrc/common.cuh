@@ -107,6 +107,26 @@ __device__ __forceinline__ int64_t load_index(const void* p, int64_t i, int is64
     return is64 ? ((const int64_t*)p)[i] : (int64_t)((const int32_t*)p)[i];
 }
 
+// The same load with the result left untouched in two 32-bit words: a software-pipelined gather loads the index of a
+// later tile and must not compute anything from it before that tile comes up (the sign extension / select of
+// load_index is scheduled right behind the load and waits for it: 13-19 % of the stall samples of the LFA kernels
+// were on that one instruction, profiles/r02_lfa_stalls.md).  index_value() resolves it at the point of use.
+struct RawIndex {
+    int lo, hi;
+};
+__device__ __forceinline__ void load_index_raw(const void* p, int64_t i, int is64, RawIndex& r) {
+    if (is64) {
+        const int2 v = ((const int2*)p)[i];
+        r.lo = v.x;
+        r.hi = v.y;
+    } else {
+        r.lo = ((const int32_t*)p)[i];
+    }
+}
+__device__ __forceinline__ int64_t index_value(const RawIndex& r, int is64) {
+    return is64 ? (int64_t)(((uint64_t)(uint32_t)r.hi << 32) | (uint64_t)(uint32_t)r.lo) : (int64_t)r.lo;
+}
+
 // (d0, d1) += a * (b0, b1) as ONE packed instruction (sm_100 FFMA2: `FFMA2 R, R.F32, UR.F32x2, R.F32x2` -- the scalar
 // multiplicand is broadcast, the weight pair comes from a uniform-register pair loaded from the constant bank).  Two
 // independent IEEE fp32 FMAs: bit-identical to two FFMA.  lfa16c_kernel is issue bound (73-76 % of the issue slots,
@@ -118,6 +138,15 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a, float b0, f
     asm("mov.b64 %0, {%1, %2};" : "=l"(cv) : "f"(d0), "f"(d1));
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(cv) : "l"(av), "l"(bv));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(cv));
+}
+
+// 2^x as ONE MUFU (ex2.approx.ftz, relative error 2^-22).  Softmax weights are taken as
+// exp(s - m) = 2^(s * log2e - m * log2e): an FFMA and a MUFU per weight (expf: ~8 instructions, __expf: 5).
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // activation codes shared with the C ABI

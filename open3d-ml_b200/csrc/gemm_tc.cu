@@ -428,13 +428,14 @@ gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
             ph_chunk[chunk & 1] ^= 1;
             tc::tc_fence_after();
             if (owns_cols) {
+                uint32_t vr[NQ][16];       // all of this thread's columns behind one wait
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    float v[16];
-                    tc::tmem_ld16(tmem_lane + (chunk & 1) * BN + colbase + q * 16, v);
+                for (int q = 0; q < NQ; ++q) tc::tmem_ld16_issue(tmem_lane + (chunk & 1) * BN + colbase + q * 16, vr[q]);
+                tc::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) racc[q * 16 + j] += v[j];
-                }
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) racc[q * 16 + j] += tc::tmem_val(vr[q][j]);
             }
             tc::tc_fence_before();
         };

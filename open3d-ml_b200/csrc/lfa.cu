@@ -22,6 +22,7 @@
 // variant plugs into the same tiles.
 #include "../../include/o3dml_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace o3dml {
@@ -452,26 +453,92 @@ struct alignas(16) Lfa16W {
 constexpr int W16_W10 = 0, W16_S10 = 80, W16_T10 = 88, W16_WL2 = 96, W16_S2 = 160, W16_T2 = 168,
               W16_WS = 176, W16_BS = 432;
 
-template <int STAGE>
-__global__ void __launch_bounds__(L16_ROWS, 4)
+// PF = gather pipelining over the groups a CTA walks (the un-pipelined kernel spent 23 % of its stall samples on the
+// two dependent round trips index -> coordinates / features, profiles/r02_lfa_stalls.md):
+//   0  none            1  the neighbour index of the next group is requested one group ahead (raw word, common.cuh)
+//   2  index two groups ahead, coordinates + feature row of the next group one group ahead (14 more registers:
+//      4 CTAs per SM instead of 5)
+#ifndef L16C_CTAS
+#define L16C_CTAS 5    // resident CTAs per SM the register allocation is held to (42 registers)
+#endif
+template <int STAGE, int PF>
+__global__ void __launch_bounds__(L16_ROWS, PF == 2 ? 4 : L16C_CTAS)
 lfa16c_kernel(const __grid_constant__ LfaParams p, const __grid_constant__ Lfa16W w, int64_t num_groups) {
     constexpr int D = 16, H = 8;
     __shared__ __align__(16) float St[D * L16_RS];      // scores, channel-major
     __shared__ __align__(16) float Xs[D * L16_RS];      // X, channel-major
     const int tid = threadIdx.x;
     const int pl = tid >> 4, j = tid & 15;
-    for (int64_t grp = blockIdx.x; grp < num_groups; grp += gridDim.x) {
-        const int64_t g = grp * L16_PTS + pl;
+    // 32-bit index arithmetic throughout (the launcher checks total < 2^31; a third of this issue-bound kernel's
+    // instructions were 64-bit address / division sequences); a neighbour index is < n_per_batch, so the low word
+    // of an int64 entry is the whole value
+    const unsigned total = (unsigned)p.total, npb = (unsigned)p.n_per_batch;
+    const unsigned ngrp = (unsigned)num_groups, gstride = gridDim.x;
+    const int* nidx32 = reinterpret_cast<const int*>(p.nidx);
+    const int ishift = p.nidx_is64 ? 1 : 0;
+    // pipeline state: (base, raw) of the group whose index is in flight, (gn, data) of the group whose rows are
+    int raw_a = 0;
+    unsigned base_a = 0;
+    bool ok_a = false;
+    int gn_b = -1;
+    float4 fb0 = make_float4(0.f, 0.f, 0.f, 0.f), fb1 = fb0;
+    float qb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    auto request_index = [&](unsigned grp_) {
+        const unsigned g_ = grp_ * L16_PTS + pl;
+        ok_a = grp_ < ngrp && g_ < total;
+        if (ok_a) {
+            base_a = g_ - g_ % npb;
+            raw_a = nidx32[((size_t)g_ * LFA_K + j) << ishift];   // stays a raw loaded word until its group comes up
+        }
+    };
+    auto request_rows = [&](unsigned grp_) {     // consumes the index requested for grp_
+        gn_b = ok_a ? (int)(base_a + (unsigned)raw_a) : -1;
+        if (gn_b >= 0) {
+            const unsigned g_ = grp_ * L16_PTS + pl;
+            const float* fr = p.feat + (size_t)(unsigned)gn_b * H;
+            fb0 = *reinterpret_cast<const float4*>(fr);
+            fb1 = *reinterpret_cast<const float4*>(fr + 4);
+            const float* cq = p.coords + (size_t)g_ * 3;
+            const float* cn = p.coords + (size_t)(unsigned)gn_b * 3;
+            qb[0] = cq[0]; qb[1] = cq[1]; qb[2] = cq[2];
+            qb[3] = cn[0]; qb[4] = cn[1]; qb[5] = cn[2];
+        }
+    };
+    if (PF >= 1) request_index(blockIdx.x);
+    if (PF == 2) {
+        request_rows(blockIdx.x);
+        request_index(blockIdx.x + gstride);
+    }
+    for (unsigned grp = blockIdx.x; grp < ngrp; grp += gstride) {
+        const unsigned g = grp * L16_PTS + pl;
         float x[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) x[c] = 0.f;
-        if (g < p.total) {
-            const int64_t b = g / p.n_per_batch;
-            const int64_t gn = b * p.n_per_batch + load_index(p.nidx, g * LFA_K + j, p.nidx_is64);
-            const float4 f0 = *reinterpret_cast<const float4*>(p.feat + (size_t)gn * H);
-            const float4 f1 = *reinterpret_cast<const float4*>(p.feat + (size_t)gn * H + 4);
-            const float qx = p.coords[3 * g], qy = p.coords[3 * g + 1], qz = p.coords[3 * g + 2];
-            const float cx = p.coords[3 * gn], cy = p.coords[3 * gn + 1], cz = p.coords[3 * gn + 2];
+        int gn = -1;
+        float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0;
+        float qx = 0.f, qy = 0.f, qz = 0.f, cx = 0.f, cy = 0.f, cz = 0.f;
+        if (PF == 2) {
+            gn = gn_b;
+            f0 = fb0; f1 = fb1;
+            qx = qb[0]; qy = qb[1]; qz = qb[2]; cx = qb[3]; cy = qb[4]; cz = qb[5];
+            request_rows(grp + gstride);                 // next group: rows in flight from here
+            request_index(grp + 2 * gstride);            // the one after: index
+        } else if (g < total) {
+            if (PF == 1) {
+                gn = (int)(base_a + (unsigned)raw_a);
+            } else {
+                gn = (int)(g - g % npb) + nidx32[((size_t)g * LFA_K + j) << ishift];
+            }
+            const float* fr = p.feat + (size_t)(unsigned)gn * H;
+            f0 = *reinterpret_cast<const float4*>(fr);
+            f1 = *reinterpret_cast<const float4*>(fr + 4);
+            const float* cq = p.coords + (size_t)g * 3;
+            const float* cn = p.coords + (size_t)(unsigned)gn * 3;
+            qx = cq[0]; qy = cq[1]; qz = cq[2];
+            cx = cn[0]; cy = cn[1]; cz = cn[2];
+        }
+        if (PF == 1) request_index(grp + gstride);
+        if (gn >= 0) {
             const float dx = qx - cx, dy = qy - cy, dz = qz - cz;
             float e[10];
             e[0] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
@@ -536,35 +603,54 @@ lfa16c_kernel(const __grid_constant__ LfaParams p, const __grid_constant__ Lfa16
 #pragma unroll
             for (int q = 0; q < 4; ++q) m = fmaxf(fmaxf(fmaxf(m, s4[q].x), s4[q].y), fmaxf(s4[q].z, s4[q].w));
             float num = 0.f, den = 0.f;
+            const float ml = -m * kLog2e;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 xv = *reinterpret_cast<const float4*>(xrow + 4 * q);
-                const float e0 = expf(s4[q].x - m), e1 = expf(s4[q].y - m);
-                const float e2 = expf(s4[q].z - m), e3 = expf(s4[q].w - m);
+                // exp(s - m) = 2^(s * log2e - m * log2e): FFMA + MUFU per weight instead of the ~8 instructions of
+                // expf (the weights are normalised right below; the tensor-core kernels do the same)
+                const float e0 = ex2_ftz(fmaf(s4[q].x, kLog2e, ml)), e1 = ex2_ftz(fmaf(s4[q].y, kLog2e, ml));
+                const float e2 = ex2_ftz(fmaf(s4[q].z, kLog2e, ml)), e3 = ex2_ftz(fmaf(s4[q].w, kLog2e, ml));
                 den += (e0 + e1) + (e2 + e3);
                 num = fmaf(e0, xv.x, num);
                 num = fmaf(e1, xv.y, num);
                 num = fmaf(e2, xv.z, num);
                 num = fmaf(e3, xv.w, num);
             }
-            if (g < p.total) p.agg[(size_t)g * D + j] = num / den;
+            if (g < total) p.agg[(size_t)g * D + j] = num / den;
         }
         __syncthreads();
     }
 }
 
-template <int STAGE>
-static int lfa16c_launch(const LfaParams& p, const Lfa16W& w, cudaStream_t st) {
+template <int STAGE, int PF>
+static int lfa16c_launch_pf(const LfaParams& p, const Lfa16W& w, cudaStream_t st) {
     const int64_t groups = ceil_div<int64_t>(p.total, L16_PTS);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t cap = (int64_t)sms * 4;
+    const int64_t cap = (int64_t)device_sm_count() * (PF == 2 ? 4 : L16C_CTAS);
     const unsigned blocks = (unsigned)(groups < cap ? groups : cap);
-    lfa16c_kernel<STAGE><<<blocks, L16_ROWS, 0, st>>>(p, w, groups);
+    lfa16c_kernel<STAGE, PF><<<blocks, L16_ROWS, 0, st>>>(p, w, groups);
     O3DML_LAUNCH_CHECK();
     o3dml_count_launches(1);
     return O3DML_OK;
+}
+
+// development hook: O3DML_LFA16_PF = 0 | 1 | 2 selects the gather pipelining depth (default below)
+static int lfa16_pf_mode() {
+    static const int mode = [] {
+        const char* e = getenv("O3DML_LFA16_PF");
+        const int m = e ? atoi(e) : 1;
+        return m < 0 ? 0 : m > 2 ? 2 : m;
+    }();
+    return mode;
+}
+
+template <int STAGE>
+static int lfa16c_launch(const LfaParams& p, const Lfa16W& w, cudaStream_t st) {
+    switch (lfa16_pf_mode()) {
+        case 0: return lfa16c_launch_pf<STAGE, 0>(p, w, st);
+        case 2: return lfa16c_launch_pf<STAGE, 2>(p, w, st);
+        default: return lfa16c_launch_pf<STAGE, 1>(p, w, st);
+    }
 }
 
 }  // namespace o3dml

@@ -24,7 +24,6 @@
 
 namespace o3dml {
 
-constexpr int LTC_THREADS = 256;
 constexpr int LTC_ROWS = 128;  // MMA M
 constexpr int LTC_K = 16;      // neighbours
 constexpr int LTC_SLICE = 32;  // channels per streamed weight slice
@@ -263,22 +262,42 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
     uint32_t ph_main[2] = {0, 0};  // parities of mbar[0] (lse2) and mbar[1] (scores)
     uint32_t ph_ring[5] = {0, 0, 0, 0, 0};  // parities of mbar[2..6]: weight ring full / free and `done` (gemm_streamed)
 
-    // TRANS kernels software-pipeline the gathers over tiles: the neighbour index of tile t+2 and the
-    // coordinates / feature rows of tile t+1 are requested at the top of tile t and land while its
-    // MMAs and epilogue run (two dependent global round trips leave the per-tile critical path).
-    constexpr bool PREF = C::TRANS;
+    // The gathers are software-pipelined over tiles (d >= 64): the neighbour index of tile t+2 and the
+    // coordinates / feature rows of tile t+1 are requested while tile t is worked on and land behind its
+    // MMAs and epilogue (two dependent global round trips leave the per-tile critical path).  d = 256 holds 64
+    // feature registers per tile: there the requests for tile t+1 go out after the rows of tile t have been stored
+    // (LATE) and the index stays a raw loaded word until its tile comes up (RAW_INDEX, common.cuh RawIndex).  The
+    // resident-weight kernels resolve the index of tile t+2 right behind its load: every warp of the CTA waits there
+    // for one L2 round trip, 13-19 % of the stall samples (profiles/r02_lfa_stalls.md) -- and taking that wait away
+    // made d = 64 SLOWER (2 x 188.6 / 217.3 us against 173.7 / 195.6 us per launch, same build otherwise; d = 128 equal):
+    // with two CTAs per SM the wait is where the other CTA gets the issue slots and the shared-memory port.
+    constexpr bool PREF = D >= 64;
+    constexpr bool LATE = C::STREAM;
+#ifdef LTC_RAW_INDEX_ALL
+    constexpr bool RAW_INDEX = true;
+#else
+    constexpr bool RAW_INDEX = C::STREAM;
+#endif
     constexpr int FCH = PREF ? (H / 8) / NPART : 1;      // feature chunks (8 channels) per thread
-    int64_t g_nx = p.total, nb_nx = -1, g_n2 = p.total, nb_n2 = -1;
+    int64_t g_nx = p.total, nb_nx = -1, g_n2 = p.total, base_n2 = -1;
+    RawIndex raw_n2 = {0, 0};
     float qc_nx[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float4 f_nx[FCH][2];
-    auto load_idx = [&](int64_t t, int64_t& g_, int64_t& nb_) {
+    auto load_idx = [&](int64_t t, int64_t& g_, int64_t& base_, RawIndex& raw_) {
         g_ = p.total;
-        nb_ = -1;
+        base_ = -1;
         if (t < p.num_tiles) {
             g_ = t * (LTC_ROWS / LTC_K) + (row >> 4);
-            if (g_ < p.total)
-                nb_ = (g_ / p.n_per_batch) * p.n_per_batch + load_index(p.nidx, g_ * LTC_K + (row & 15), p.nidx_is64);
+            if (g_ < p.total) {
+                base_ = (g_ / p.n_per_batch) * p.n_per_batch;
+                if (RAW_INDEX) load_index_raw(p.nidx, g_ * LTC_K + (row & 15), p.nidx_is64, raw_);
+                else base_ += load_index(p.nidx, g_ * LTC_K + (row & 15), p.nidx_is64);
+            }
         }
+    };
+    auto resolve = [&](int64_t base_, const RawIndex& raw_) -> int64_t {
+        if (!RAW_INDEX) return base_;
+        return base_ >= 0 ? base_ + index_value(raw_, p.nidx_is64) : (int64_t)-1;
     };
     auto load_data = [&](int64_t g_, int64_t nb_, float* qc, float4 (*f)[2]) {
         if (nb_ >= 0) {
@@ -297,54 +316,38 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
             for (int i = 0; i < FCH; ++i) f[i][0] = f[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    if (PREF) {
-        load_idx(blockIdx.x, g_nx, nb_nx);
+    // requests for the tile after `tile` (index resolved now, one tile after its load) and the index of the one after
+    auto advance = [&](int64_t tile) {
+        g_nx = g_n2;
+        nb_nx = resolve(base_n2, raw_n2);
         load_data(g_nx, nb_nx, qc_nx, f_nx);
-        load_idx((int64_t)blockIdx.x + gridDim.x, g_n2, nb_n2);
+        load_idx(tile + 2 * (int64_t)gridDim.x, g_n2, base_n2, raw_n2);
+    };
+    if (PREF) {
+        load_idx(blockIdx.x, g_nx, base_n2, raw_n2);
+        nb_nx = resolve(base_n2, raw_n2);
+        load_data(g_nx, nb_nx, qc_nx, f_nx);
+        load_idx((int64_t)blockIdx.x + gridDim.x, g_n2, base_n2, raw_n2);
     }
 
-    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        // ---------------- neighbour id + 10-channel encoding of this thread's row
-        int64_t g = tile * (LTC_ROWS / LTC_K) + (row >> 4);
-        int64_t nb = -1;
-        float e[10];
-        float4 f_cur[FCH][2];
+    // 10-channel relative position encoding of this thread's row (randlanet.py:586-600)
+    auto encode = [&](int64_t nb_, const float* qc, float* e) {
 #pragma unroll
         for (int q = 0; q < 10; ++q) e[q] = 0.f;
-        if (PREF) {
-            g = g_nx;
-            nb = nb_nx;
-            float qc[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) qc[i] = qc_nx[i];
-#pragma unroll
-            for (int i = 0; i < FCH; ++i) { f_cur[i][0] = f_nx[i][0]; f_cur[i][1] = f_nx[i][1]; }
-            g_nx = g_n2;
-            nb_nx = nb_n2;
-            load_data(g_nx, nb_nx, qc_nx, f_nx);                       // tile t+1: in flight from here
-            load_idx(tile + 2 * (int64_t)gridDim.x, g_n2, nb_n2);      // tile t+2: index
-            if (nb >= 0) {
-                const float dx = qc[0] - qc[3], dy = qc[1] - qc[4], dz = qc[2] - qc[5];
-                e[0] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-                e[1] = dx; e[2] = dy; e[3] = dz;
-                e[4] = qc[0]; e[5] = qc[1]; e[6] = qc[2];
-                e[7] = qc[3]; e[8] = qc[4]; e[9] = qc[5];
-            }
-        } else if (g < p.total) {
-            const int64_t b = g / p.n_per_batch;
-            nb = b * p.n_per_batch + load_index(p.nidx, g * LTC_K + (row & 15), p.nidx_is64);
-            const float qx = p.coords[3 * g], qy = p.coords[3 * g + 1], qz = p.coords[3 * g + 2];
-            const float cx = p.coords[3 * nb], cy = p.coords[3 * nb + 1], cz = p.coords[3 * nb + 2];
-            const float dx = qx - cx, dy = qy - cy, dz = qz - cz;
+        if (nb_ >= 0) {
+            const float dx = qc[0] - qc[3], dy = qc[1] - qc[4], dz = qc[2] - qc[5];
             e[0] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
             e[1] = dx; e[2] = dy; e[3] = dz;
-            e[4] = qx; e[5] = qy; e[6] = qz;
-            e[7] = cx; e[8] = cy; e[9] = cz;
+            e[4] = qc[0]; e[5] = qc[1]; e[6] = qc[2];
+            e[7] = qc[3]; e[8] = qc[4]; e[9] = qc[5];
         }
-        // ---------------- r1 = lrelu(BN(W10 . enc)), 8 outputs at a time, straight into the operand:
-        //   stage 1            -> channels [H, D) of A
-        //   stage 2, tensor    -> channels [0, H) of A (A operand of the lse2 GEMM)
-        //   stage 2, H < 16    -> r2 = lrelu(BN(Wl2 . r1)) in registers -> channels [H, D)
+    };
+    // r1 = lrelu(BN(W10 . enc)), 8 outputs at a time, straight into an operand region of H channels (chunk-major,
+    // chunk `ch` of the region at dst + ch * LTC_ROWS * 16):
+    //   stage 1            -> channels [H, D) of A
+    //   stage 2, tensor    -> channels [0, H) of A, the A operand of the lse2 GEMM
+    //   stage 2, H < 16    -> r2 = lrelu(BN(Wl2 . r1)) in registers -> channels [H, D)
+    auto locse = [&](const float* e, uint8_t* dst_hi, uint8_t* dst_lo) {
         for (int ch = half; ch < H / 8; ch += NPART) {
             float r[8];
 #pragma unroll
@@ -358,35 +361,95 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
                 ffma2(r[4], r[5], e[q], wb.x, wb.y);
                 ffma2(r[6], r[7], e[q], wb.z, wb.w);
             }
+            {   // folded BN + LeakyReLU; scale / shift as four LDS.128
+                const float4 sa = *reinterpret_cast<const float4*>(&W10[10 * H + ch * 8]);
+                const float4 sb = *reinterpret_cast<const float4*>(&W10[10 * H + ch * 8 + 4]);
+                const float4 ta = *reinterpret_cast<const float4*>(&W10[11 * H + ch * 8]);
+                const float4 tb = *reinterpret_cast<const float4*>(&W10[11 * H + ch * 8 + 4]);
+                const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                const float sh[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int o = ch * 8 + j;
-                const float a = fmaf(r[j], W10[10 * H + o], W10[11 * H + o]);
-                r[j] = a >= 0.f ? a : 0.2f * a;
-            }
-            int dst_chunk = H / 8 + ch;
-            if (STAGE == 2) {
-                if (C::MMA2) {
-                    dst_chunk = ch;
-                } else {  // H == 8: one chunk holds all of r1
-                    float r2[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float a = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) a = fmaf(r[i], ST2[2 * H + i * H + j], a);
-                        a = fmaf(a, ST2[j], ST2[H + j]);
-                        r2[j] = a >= 0.f ? a : 0.2f * a;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] = r2[j];
+                for (int j = 0; j < 8; ++j) {
+                    const float a = fmaf(r[j], sc[j], sh[j]);
+                    r[j] = a >= 0.f ? a : 0.2f * a;
                 }
+            }
+            if (STAGE == 2 && !C::MMA2) {  // H == 8: one chunk holds all of r1
+                float r2[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a = fmaf(r[i], ST2[2 * H + i * H + j], a);
+                    a = fmaf(a, ST2[j], ST2[H + j]);
+                    r2[j] = a >= 0.f ? a : 0.2f * a;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = r2[j];
             }
             uint4 hi, lo;
             tc::split8(r, hi, lo);
-            *reinterpret_cast<uint4*>(a_hi + tc::op_off(LTC_ROWS, row, dst_chunk)) = hi;
-            *reinterpret_cast<uint4*>(a_lo + tc::op_off(LTC_ROWS, row, dst_chunk)) = lo;
+            *reinterpret_cast<uint4*>(dst_hi + tc::op_off(LTC_ROWS, row, ch)) = hi;
+            *reinterpret_cast<uint4*>(dst_lo + tc::op_off(LTC_ROWS, row, ch)) = lo;
         }
+    };
+    // r1 goes to channels [0, H) when the tensor core computes lse2 from it, else (r1 of stage 1, r2 of the d = 16
+    // register path) to channels [H, D)
+    constexpr uint32_t R1_OFF = (STAGE == 2 && C::MMA2) ? 0u : (uint32_t)(H / 8) * LTC_ROWS * 16;
+
+    for (int64_t tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        // ---------------- neighbour id + encoding + LocSE MLP of this thread's row
+        int64_t g = tile * (LTC_ROWS / LTC_K) + (row >> 4);
+        int64_t nb = -1;
+        float4 f_cur[FCH][2];
+        if (PREF) {
+            g = g_nx;
+            nb = nb_nx;
+            float qc[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) qc[i] = qc_nx[i];
+#pragma unroll
+            for (int i = 0; i < FCH; ++i) { f_cur[i][0] = f_nx[i][0]; f_cur[i][1] = f_nx[i][1]; }
+            if (!LATE) advance(tile);        // tile t+1: data in flight from here; tile t+2: index
+            float e[10];
+            encode(nb, qc, e);
+            locse(e, a_hi + R1_OFF, a_lo + R1_OFF);
+        } else {
+            float qc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (g < p.total) {
+                const int64_t b = g / p.n_per_batch;
+                nb = b * p.n_per_batch + load_index(p.nidx, g * LTC_K + (row & 15), p.nidx_is64);
+                qc[0] = p.coords[3 * g]; qc[1] = p.coords[3 * g + 1]; qc[2] = p.coords[3 * g + 2];
+                qc[3] = p.coords[3 * nb]; qc[4] = p.coords[3 * nb + 1]; qc[5] = p.coords[3 * nb + 2];
+            }
+            float e[10];
+            encode(nb, qc, e);
+            locse(e, a_hi + R1_OFF, a_lo + R1_OFF);
+        }
+        // gathered neighbour features -> channels [0, H) of A
+        auto store_features = [&]() {
+#pragma unroll
+            for (int ch = half, fi = 0; ch < H / 8; ch += NPART, ++fi) {
+                float x[8];
+                if (PREF) {
+                    const float4 v0 = f_cur[fi < FCH ? fi : 0][0], v1 = f_cur[fi < FCH ? fi : 0][1];
+                    x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                    x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                } else if (nb >= 0) {
+                    const float4 v0 = *reinterpret_cast<const float4*>(p.feat + (size_t)nb * H + ch * 8);
+                    const float4 v1 = *reinterpret_cast<const float4*>(p.feat + (size_t)nb * H + ch * 8 + 4);
+                    x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+                    x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+                }
+                uint4 hi, lo;
+                tc::split8(x, hi, lo);
+                *reinterpret_cast<uint4*>(a_hi + tc::op_off(LTC_ROWS, row, ch)) = hi;
+                *reinterpret_cast<uint4*>(a_lo + tc::op_off(LTC_ROWS, row, ch)) = lo;
+            }
+        };
 
         // ---------------- stage 2: r2 = lrelu(BN(Wl2 . r1)) on the tensor core -> channels [H, D)
         if (C::MMA2) {
@@ -405,42 +468,40 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
                 ph_main[0] ^= 1;
                 tc::tc_fence_after();
             }
-            for (int c0 = half * 8; c0 < H; c0 += 8 * NPART) {
-                float v[8];
-                tc::tmem_ld8(tmem_lane + LSE2_COL + c0, v);
+            constexpr int NR2 = H / (8 * NPART) > 0 ? H / (8 * NPART) : 1;   // 8-column groups of r2 per thread
+            constexpr int NB = NR2 > 4 ? 4 : NR2;                            // loads behind one wait
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float a = fmaf(v[j], ST2[c0 + j], ST2[H + c0 + j]);
-                    v[j] = a >= 0.f ? a : 0.2f * a;
+            for (int b0 = 0; b0 < NR2; b0 += NB) {
+                uint32_t vr[NB][8];
+#pragma unroll
+                for (int i = 0; i < NB; ++i)
+                    tc::tmem_ld8_issue(tmem_lane + LSE2_COL + (half + (b0 + i) * NPART) * 8, vr[i]);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < NB; ++i) {
+                    const int c0 = (half + (b0 + i) * NPART) * 8;
+                    float v[8];
+                    const float4 sa = *reinterpret_cast<const float4*>(&ST2[c0]);
+                    const float4 sb = *reinterpret_cast<const float4*>(&ST2[c0 + 4]);
+                    const float4 ta = *reinterpret_cast<const float4*>(&ST2[H + c0]);
+                    const float4 tb = *reinterpret_cast<const float4*>(&ST2[H + c0 + 4]);
+                    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                    const float sh[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = fmaf(tc::tmem_val(vr[i][j]), sc[j], sh[j]);
+                        v[j] = a >= 0.f ? a : 0.2f * a;
+                    }
+                    uint4 hi, lo;
+                    tc::split8(v, hi, lo);
+                    *reinterpret_cast<uint4*>(a_hi + tc::op_off(LTC_ROWS, row, (H + c0) / 8)) = hi;
+                    *reinterpret_cast<uint4*>(a_lo + tc::op_off(LTC_ROWS, row, (H + c0) / 8)) = lo;
                 }
-                uint4 hi, lo;
-                tc::split8(v, hi, lo);
-                *reinterpret_cast<uint4*>(a_hi + tc::op_off(LTC_ROWS, row, (H + c0) / 8)) = hi;
-                *reinterpret_cast<uint4*>(a_lo + tc::op_off(LTC_ROWS, row, (H + c0) / 8)) = lo;
             }
         }
-        // ---------------- gathered neighbour features -> channels [0, H)  (overwrites r1 in stage 2:
-        // the lse2 MMAs that read it have completed)
-        for (int ch = half, fi = 0; ch < H / 8; ch += NPART, ++fi) {
-            float x[8];
-            if (PREF) {
-                const float4 v0 = f_cur[fi < FCH ? fi : 0][0], v1 = f_cur[fi < FCH ? fi : 0][1];
-                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-            } else if (nb >= 0) {
-                const float4 v0 = *reinterpret_cast<const float4*>(p.feat + (size_t)nb * H + ch * 8);
-                const float4 v1 = *reinterpret_cast<const float4*>(p.feat + (size_t)nb * H + ch * 8 + 4);
-                x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-                x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = 0.f;
-            }
-            uint4 hi, lo;
-            tc::split8(x, hi, lo);
-            *reinterpret_cast<uint4*>(a_hi + tc::op_off(LTC_ROWS, row, ch)) = hi;
-            *reinterpret_cast<uint4*>(a_lo + tc::op_off(LTC_ROWS, row, ch)) = lo;
-        }
+        // (the features overwrite r1 in stage 2: the lse2 MMAs that read it have completed)
+        store_features();
+        if (PREF && LATE) advance(tile);     // lands behind the score GEMM and the epilogue
         tc::fence_async_smem();
         tc::tc_fence_before();
         __syncthreads();
@@ -474,15 +535,25 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
             for (int q = 0; q < 2; ++q) {
                 const int pt = pbase + q;
                 float s[16], x[16];
-                tc::tmem_ld16(tmem_lane + pt * LTC_K, s);
-                tc::tmem_ld16(tmem_lane + LTC_ROWS + pt * LTC_K, x);
+                {
+                    uint32_t sr[16], xr[16];     // scores and X^T of the point behind one wait
+                    tc::tmem_ld16_issue(tmem_lane + pt * LTC_K, sr);
+                    tc::tmem_ld16_issue(tmem_lane + LTC_ROWS + pt * LTC_K, xr);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        s[j] = tc::tmem_val(sr[j]);
+                        x[j] = tc::tmem_val(xr[j]);
+                    }
+                }
                 float m = s[0];
 #pragma unroll
                 for (int j = 1; j < 16; ++j) m = fmaxf(m, s[j]);
                 float num = 0.f, den = 0.f;
+                const float ml = -m * kLog2e;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float ev = __expf(s[j] - m);
+                    const float ev = ex2_ftz(fmaf(s[j], kLog2e, ml));
                     den += ev;
                     num = fmaf(ev, x[j], num);
                 }
@@ -519,7 +590,7 @@ lfa_pool_tc_kernel(const __grid_constant__ LfaTcParams p) {
                 const int m_hi = __reduce_max_sync(0xffffffffu, upper ? o : INT_MIN);
                 int m = upper ? m_hi : m_lo;
                 m ^= (m >> 31) & 0x7fffffff;
-                const float ev = __expf(s[i] - __int_as_float(m));
+                const float ev = ex2_ftz(fmaf(s[i], kLog2e, -__int_as_float(m) * kLog2e));
                 den[i] = ev;
                 num[i] = ev * x[i];
 #ifdef O3DML_DEBUG_NAN

@@ -109,13 +109,15 @@ __device__ __forceinline__ void rt_issue(uint32_t tmem, uint32_t wbase, uint64_t
 // accumulator of the layer -> folded BN / bias (+ LeakyReLU) -> registers
 template <int N, bool ACT>
 __device__ __forceinline__ void rt_load_d(uint32_t tmem_lane, const RlTailParams& p, int layer, float* a) {
+    uint32_t vr[N / 16][16];        // the whole accumulator row behind one wait (this read is on the layer chain)
+#pragma unroll
+    for (int q = 0; q < N / 16; ++q) tc::tmem_ld16_issue(tmem_lane + RT_D + q * 16, vr[q]);
+    tc::tmem_ld_wait();
 #pragma unroll
     for (int q = 0; q < N / 16; ++q) {
-        float v[16];
-        tc::tmem_ld16(tmem_lane + RT_D + q * 16, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            float y = fmaf(v[j], p.scale[layer][q * 16 + j], p.shift[layer][q * 16 + j]);
+            float y = fmaf(tc::tmem_val(vr[q][j]), p.scale[layer][q * 16 + j], p.shift[layer][q * 16 + j]);
             if (ACT) y = y >= 0.f ? y : y * p.slope;
             a[q * 16 + j] = y;
         }

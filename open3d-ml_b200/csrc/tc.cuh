@@ -140,6 +140,33 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Issue-only forms: several loads in flight behind ONE tcgen05.wait::ld (tmem_ld16 / tmem_ld8 pay a TMEM round trip
+// each).  The destination registers are defined after tmem_ld_wait(); read them through tmem_val(), which pins the
+// read behind the wait in program order.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tmem_val(uint32_t& r) {
+    asm volatile("" : "+r"(r));
+    return __uint_as_float(r);
+}
+
 // ---- fp32 -> (h1, h2) split -----------------------------------------------------------------
 __device__ __forceinline__ void split_f16(float x, __half& h1, __half& h2) {
     x = fminf(fmaxf(x, -65504.f), 65504.f);
