@@ -451,7 +451,7 @@ extern "C" int o3dml_pp_pfn_scatter(const float* points, int point_stride, int p
     if (num_voxels_bound <= 0) return O3DML_OK;
     int64_t warps_needed = num_voxels_bound;
     int64_t blocks = ceil_div<int64_t>(warps_needed, 8);
-    int64_t cap = (int64_t)kNumSMs * 8;  // 8 resident CTAs of 256 threads per SM
+    int64_t cap = (int64_t)device_sm_count() * 8;  // 8 resident CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
     pp_pfn_scatter_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(
         points, point_stride, point_channels, voxel_coords, voxel_row_splits, voxel_point_indices,

@@ -10,8 +10,8 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-run() { tag=$1; flags=$2; shift; shift; O3DML_NVCC_EXTRA="$flags" python open3d-ml_b200/build.py --force > /dev/null 2>gpurun_out/ab3_$tag.build || echo build failed;
-  O3DML_NVCC_EXTRA="$flags" timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu "$@" 2>gpurun_out/ab3_$tag.err | tail -1 > gpurun_out/ab3_$tag.json; summ gpurun_out/ab3_$tag.json; }
+run() { tag=$1; flags=$2; shift; shift; O3DML_NVCC_EXTRA="$flags" python open3d-ml_b200/build.py --force > /dev/null 2>gpurun_out/abc_$tag.build || echo build failed;
+  O3DML_NVCC_EXTRA="$flags" timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu "$@" 2>gpurun_out/abc_$tag.err | tail -1 > gpurun_out/abc_$tag.json; summ gpurun_out/abc_$tag.json; }
 python open3d-ml_b200/build.py --force > /dev/null
 timeout 600 python -m pytest tests/test_gpu_lfa_tc.py tests/test_gpu_models.py tests/test_gpu_dense.py -q -x 2>&1 | tail -5
 run base ""

@@ -10,8 +10,8 @@ except Exception as e:
     print(sys.argv[1], "FAILED", e)
 PY
 }
-run() { tag=$1; flags=$2; O3DML_NVCC_EXTRA="$flags" python open3d-ml_b200/build.py --force > /dev/null 2>gpurun_out/ab2_$tag.build || echo build failed; 
-  O3DML_NVCC_EXTRA="$flags" timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu 2>gpurun_out/ab2_$tag.err | tail -1 > gpurun_out/ab2_$tag.json; summ gpurun_out/ab2_$tag.json; }
+run() { tag=$1; flags=$2; O3DML_NVCC_EXTRA="$flags" python open3d-ml_b200/build.py --force > /dev/null 2>gpurun_out/ab_$tag.build || echo build failed; 
+  O3DML_NVCC_EXTRA="$flags" timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu 2>gpurun_out/ab_$tag.err | tail -1 > gpurun_out/ab_$tag.json; summ gpurun_out/ab_$tag.json; }
 run base ""
 run eager "-DLTC_EAGER_INDEX"
 run expf "-DLTC_EXPF"
