@@ -76,11 +76,18 @@ class PipelinedRunner:
         for k, host in enumerate(batches):
             s = k % self.SLOTS
             # ---- inputs of batch k: H2D on the copy stream
+            fresh = None
             if self._dev_in[s] is None or not _same_layout(self._dev_in[s], host):
                 if in_free[s] is not None:
                     in_free[s].synchronize()
                 self._dev_in[s] = _alloc_like(host, self.device)
+                # The caching allocator hands out blocks in the order of the ALLOCATING stream (main): a recycled block
+                # may still be read by kernels queued on main.  The copy stream must not write it before they are done.
+                fresh = torch.cuda.Event()
+                fresh.record(main)
             with torch.cuda.stream(self.s_in):
+                if fresh is not None:
+                    self.s_in.wait_event(fresh)
                 if in_free[s] is not None:
                     self.s_in.wait_event(in_free[s])
                 dev_in = _copy_tree(self._dev_in[s], host)
