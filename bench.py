@@ -694,7 +694,10 @@ def run_b200(args, wl):
                                                     "library kernels, 1 unit; informational: what the reference's own torch code "
                                                     "gets from a B200 without this library")
         except Exception as e:  # noqa: BLE001
-            extra["gpu_eager_baseline"] = dict(unavailable=str(e)[:200])
+            msg = str(e)[:200]
+            if "numpy" in msg:
+                msg = "the torch port of this workload voxelizes on the host with numpy: no GPU-eager arm"
+            extra["gpu_eager_baseline"] = dict(unavailable=msg)
     best = max(e2e_modes, key=lambda k: e2e_modes[k]["value"])
     e2e = dict(e2e_modes[best], unit="Mpoints/s", entry=best,
                d2h_bytes_per_step=sum(nbytes(o) for o in outs),
